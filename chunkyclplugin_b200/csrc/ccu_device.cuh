@@ -1,0 +1,605 @@
+// ccu_device.cuh - device-side scene description and the traversal / shading functions.
+//
+// Written from the behaviour of the reference kernels (cited per function, paths under
+// /root/reference/src/main/opencl/kernel/include/); structure, data layout and control flow are ours.
+#pragma once
+#include "ccu_math.cuh"
+
+namespace ccu {
+
+#define CCU_ANY_TYPE 0x7FFFFFFE   // block.h:32
+
+struct DScene {
+    // octree (reference numbering: ClSceneLoader.java:56-59)
+    const int *__restrict__ tree;
+    int depth;
+    // palettes (reference packed layouts)
+    const int *__restrict__ block_palette;
+    int block_palette_len;
+    const int *__restrict__ quad_models;
+    const int *__restrict__ aabb_models;
+    const int *__restrict__ mat_palette;
+    const int *__restrict__ world_bvh;
+    const int *__restrict__ actor_bvh;
+    const int *__restrict__ trigs;
+    int world_bvh_empty, actor_bvh_empty;   // result of the bvh.h:23-32 probe, evaluated once at commit
+    // atlas: RGBA8, tile-linear (16x16 texel tiles contiguous), clamp extents = image extents
+    const uchar4 *__restrict__ atlas;
+    int atlas_w, atlas_h, atlas_layers, atlas_tiles_x, atlas_tiles_y;
+    // sky: RGBA8 res x res
+    const uchar4 *__restrict__ sky;
+    int sky_res;
+    float sky_intensity;
+    // sun (Sun_new sky.h:19-40 evaluated once on the device at commit)
+    int sun_flags, sun_tex_size, sun_tex;
+    float sun_intensity, sun_radius_cos;
+    float3 su, sv, sw;
+    // camera
+    int projector_type;
+    float cam[15];
+    const float *__restrict__ rays;
+    int width, height;
+    // launch parameters
+    int draw_depth, max_depth;
+    float emitter_scale;
+};
+
+struct Record {      // IntersectionRecord, wavefront.h:37-78
+    float distance;
+    int material;
+    float3 normal;
+    float3 point;
+    float4 color;
+    float emittance;
+};
+
+struct HitInfo {     // first-hit bookkeeping, not part of the reference's record
+    int node;
+    int kind;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// images
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 color_from_argb(uint32_t argb) {   // utils.h:6-14
+    float4 c;
+    c.w = (float)((argb >> 24) & 0xFF) / 256.0f;
+    c.x = (float)((argb >> 16) & 0xFF) / 256.0f;
+    c.y = (float)((argb >> 8) & 0xFF) / 256.0f;
+    c.z = (float)(argb & 0xFF) / 256.0f;
+    return c;
+}
+__device__ __forceinline__ float4 unorm8(uchar4 t) {
+    return make_float4((float)t.x / 255.0f, (float)t.y / 255.0f, (float)t.z / 255.0f, (float)t.w / 255.0f);
+}
+// textureAtlas.h:10-16: nearest / clamp-to-edge / integer coordinates
+__device__ __forceinline__ float4 atlas_read_xy(const DScene &s, int x, int y, int location) {
+    x += ((location >> 22) & 0x1FF) * 16;
+    y += ((location >> 13) & 0x1FF) * 16;
+    int d = location & 0x7FFFF;
+    x = min(max(x, 0), s.atlas_w - 1);
+    y = min(max(y, 0), s.atlas_h - 1);
+    d = min(max(d, 0), s.atlas_layers - 1);
+    size_t tile = ((size_t)d * s.atlas_tiles_y + (y >> 4)) * s.atlas_tiles_x + (x >> 4);
+    return unorm8(__ldg(s.atlas + tile * 256 + ((y & 15) << 4) + (x & 15)));
+}
+// textureAtlas.h:18-28
+__device__ __forceinline__ float4 atlas_read_uv(const DScene &s, float u, float v, int location, int size) {
+    int width = (size >> 16) & 0xFFFF;
+    int height = size & 0xFFFF;
+    v = 1.0f - v;
+    int x = min(max(f2i((u - CCU_EPS) * (float)width), 0), width - 1);
+    int y = min(max(f2i((v - CCU_EPS) * (float)height), 0), height - 1);
+    return atlas_read_xy(s, x, y, location);
+}
+// sky.h:95 sampler semantics (OpenCL 1.2 s8.2: normalised, mirrored repeat, linear), fp32 weights
+__device__ __forceinline__ void sky_axis(float s, int w, int &i0, int &i1, float &a) {
+    float sp = 2.0f * rintf(0.5f * s);
+    sp = fabsf(s - sp);
+    float u = sp * (float)w;
+    float um = u - 0.5f;
+    float fl = floorf(um);
+    int j0 = f2i(fl);
+    int j1 = j0 + 1;
+    a = um - fl;
+    i0 = j0 < 0 ? 0 : j0;
+    i1 = j1 > w - 1 ? w - 1 : j1;
+}
+__device__ __forceinline__ float4 sky_read(const DScene &s, float cs, float ct) {
+    int w = s.sky_res, i0, i1, j0, j1;
+    float a, b;
+    sky_axis(cs, w, i0, i1, a);
+    sky_axis(ct, w, j0, j1, b);
+    float4 t00 = unorm8(__ldg(s.sky + j0 * w + i0));
+    float4 t10 = unorm8(__ldg(s.sky + j0 * w + i1));
+    float4 t01 = unorm8(__ldg(s.sky + j1 * w + i0));
+    float4 t11 = unorm8(__ldg(s.sky + j1 * w + i1));
+    float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+    float4 r;
+    r.x = ((w00 * t00.x + w10 * t10.x) + w01 * t01.x) + w11 * t11.x;
+    r.y = ((w00 * t00.y + w10 * t10.y) + w01 * t01.y) + w11 * t11.y;
+    r.z = ((w00 * t00.z + w10 * t10.z) + w01 * t01.z) + w11 * t11.z;
+    r.w = ((w00 * t00.w + w10 * t10.w) + w01 * t01.w) + w11 * t11.w;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// material.h:31-82
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool material_sample(const DScene &s, int material, Record &rec, float u, float v) {
+    const int *m = s.mat_palette + material;
+    uint32_t flags = __ldg(m), tint = __ldg(m + 1), tex_size = __ldg(m + 2), col = __ldg(m + 3), normal_emittance = __ldg(m + 4);
+    float4 color;
+    if (flags & 4u) color = atlas_read_uv(s, u, v, (int)col, (int)tex_size);
+    else color = color_from_argb(col);
+    if (color.w > CCU_EPS) rec.color = color;
+    else return false;
+    uint32_t tt = tint >> 24;
+    if (tt == 0xFF || (tt >= 1 && tt <= 3)) {
+        uint32_t argb = tt == 0xFF ? tint : (tt == 1 ? 0xFF71A74Du : (tt == 2 ? 0xFF8EB971u : 0xFF3F76E4u));
+        float4 t = color_from_argb(argb);
+        rec.color.x *= t.x; rec.color.y *= t.y; rec.color.z *= t.z; rec.color.w *= t.w;
+    }
+    if (flags & 2u) rec.emittance = atlas_read_uv(s, u, v, (int)normal_emittance, (int)tex_size).w;
+    else rec.emittance = (float)((double)(normal_emittance & 0xFF) / 255.0);   // double literal in the reference (material.h:79)
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// primitives.h
+// ------------------------------------------------------------------------------------------------------
+struct Box { float xmin, xmax, ymin, ymax, zmin, zmax; };
+
+// primitives.h:30-48
+__device__ __forceinline__ float box_entry(const Box &b, float3 o, float3 inv) {
+    float t1x = (b.xmin - o.x) * inv.x, t1y = (b.ymin - o.y) * inv.y, t1z = (b.zmin - o.z) * inv.z;
+    float t2x = (b.xmax - o.x) * inv.x, t2y = (b.ymax - o.y) * inv.y, t2z = (b.zmax - o.z) * inv.z;
+    float tmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
+    float tmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+    return (tmax < tmin) ? nanf_() : tmin;
+}
+// primitives.h:52-61
+__device__ __forceinline__ float box_exit(const Box &b, float3 o, float3 inv) {
+    float t1x = (b.xmin - o.x) * inv.x, t1y = (b.ymin - o.y) * inv.y, t1z = (b.zmin - o.z) * inv.z;
+    float t2x = (b.xmax - o.x) * inv.x, t2y = (b.ymax - o.y) * inv.y, t2z = (b.zmax - o.z) * inv.z;
+    return fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+}
+// primitives.h:66-112 (MAP2 = false) / :117-162 (MAP2 = true); later face matches overwrite earlier ones
+template <bool MAP2>
+__device__ __forceinline__ float box_full(const Box &b, float3 origin, float3 dir, float3 inv, float3 &normal, float &u, float &v) {
+    float t1x = (b.xmin - origin.x) * inv.x, t1y = (b.ymin - origin.y) * inv.y, t1z = (b.zmin - origin.z) * inv.z;
+    float t2x = (b.xmax - origin.x) * inv.x, t2y = (b.ymax - origin.y) * inv.y, t2z = (b.zmax - origin.z) * inv.z;
+    float tmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
+    float tmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+    if (tmax < tmin) return nanf_();
+    float3 o = origin + dir * tmin;
+    if (!MAP2) {
+        float dx = 1.0f / (b.xmax - b.xmin), dy = 1.0f / (b.ymax - b.ymin), dz = 1.0f / (b.zmax - b.zmin);
+        if (t1x == tmin) { u = 1.0f - (o.z - b.zmin) * dz; v = (o.y - b.ymin) * dy; normal = f3(-1, 0, 0); }
+        if (t2x == tmin) { u = (o.z - b.zmin) * dz; v = (o.y - b.ymin) * dy; normal = f3(1, 0, 0); }
+        if (t1y == tmin) { u = (o.x - b.xmin) * dx; v = 1.0f - (o.z - b.zmin) * dz; normal = f3(0, -1, 0); }
+        if (t2y == tmin) { u = (o.x - b.xmin) * dx; v = (o.z - b.zmin) * dz; normal = f3(0, 1, 0); }
+        if (t1z == tmin) { u = (o.x - b.xmin) * dx; v = (o.y - b.ymin) * dy; normal = f3(0, 0, -1); }
+        if (t2z == tmin) { u = 1.0f - (o.x - b.xmin) * dx; v = (o.y - b.ymin) * dy; normal = f3(0, 0, 1); }
+    } else {
+        if (t1x == tmin) { u = o.z; v = o.y; normal = f3(-1, 0, 0); }
+        if (t2x == tmin) { u = 1.0f - o.z; v = o.y; normal = f3(1, 0, 0); }
+        if (t1y == tmin) { u = o.x; v = o.z; normal = f3(0, -1, 0); }
+        if (t2y == tmin) { u = o.x; v = 1.0f - o.z; normal = f3(0, 1, 0); }
+        if (t1z == tmin) { u = 1.0f - o.x; v = o.y; normal = f3(0, 0, -1); }
+        if (t2z == tmin) { u = o.x; v = o.y; normal = f3(0, 0, 1); }
+    }
+    return tmin;
+}
+
+// primitives.h:200-260.  +z face: the reference reads an uninitialised material; defined as 0 / flags 0.
+__device__ __forceinline__ float textured_box(const int *model, float distance, float3 origin, float3 dir, float3 inv,
+                                              float3 &normal, float &u, float &v, int &material) {
+    Box b = {i2f(__ldg(model + 0)), i2f(__ldg(model + 1)), i2f(__ldg(model + 2)), i2f(__ldg(model + 3)), i2f(__ldg(model + 4)), i2f(__ldg(model + 5))};
+    float3 n = f3(0, 0, 0);
+    float tu = 0, tv = 0;
+    float dist = box_full<true>(b, origin, dir, inv, n, tu, tv);
+    if (dist >= distance || dist < -CCU_EPS) return nanf_();
+    if (is_nan(dist)) return nanf_();
+    int bflags = __ldg(model + 6);
+    int slot = -1, flags = 0;
+    if (n.z == -1.0f) { slot = 7; flags = bflags; }
+    if (n.x == 1.0f) { slot = 8; flags = bflags >> 4; }
+    if (n.z == -1.0f) { slot = 9; flags = bflags >> 8; }
+    if (n.x == -1.0f) { slot = 10; flags = bflags >> 12; }
+    if (n.y == 1.0f) { slot = 11; flags = bflags >> 16; }
+    if (n.y == -1.0f) { slot = 12; flags = bflags >> 20; }
+    if (flags & 8) return nanf_();
+    if (flags & 4) tu = 1.0f - tu;
+    if (flags & 2) tv = 1.0f - tv;
+    if (flags & 1) { float t = tu; tu = tv; tv = t; }
+    material = slot < 0 ? 0 : __ldg(model + slot);
+    normal = n; u = tu; v = tv;
+    return dist;
+}
+
+// primitives.h:274-319
+__device__ __forceinline__ float quad_hit(const int *q, float distance, float3 origin, float3 dir, float3 &normal, float &u, float &v) {
+    float3 qo = f3(i2f(__ldg(q + 0)), i2f(__ldg(q + 1)), i2f(__ldg(q + 2)));
+    float3 xv = f3(i2f(__ldg(q + 3)), i2f(__ldg(q + 4)), i2f(__ldg(q + 5)));
+    float3 yv = f3(i2f(__ldg(q + 6)), i2f(__ldg(q + 7)), i2f(__ldg(q + 8)));
+    float3 n = normalize3(cross3(xv, yv));
+    float denom = dot3(dir, n);
+    if (denom < -CCU_EPS) {
+        float t = -(dot3(origin, n) - dot3(n, qo)) / denom;
+        if (t > -CCU_EPS && t < distance) {
+            float3 pt = (origin + dir * t) - qo;
+            float uu = dot3(pt, xv) / dot3(xv, xv);
+            float vv = dot3(pt, yv) / dot3(yv, yv);
+            if (uu >= 0 && uu <= 1 && vv >= 0 && vv <= 1) {
+                u = i2f(__ldg(q + 9)) + (uu * i2f(__ldg(q + 10)));
+                v = i2f(__ldg(q + 11)) + (vv * i2f(__ldg(q + 12)));
+                normal = n;
+                return t;
+            }
+        }
+    }
+    return nanf_();
+}
+
+// primitives.h:335-409 (Moeller-Trumbore on pre-stored edges)
+__device__ __forceinline__ float triangle_hit(const int *t, float distance, float3 origin, float3 dir, float3 &normal,
+                                              float &ou, float &ov, int &material) {
+    int flags = __ldg(t);
+    float3 e1 = f3(i2f(__ldg(t + 1)), i2f(__ldg(t + 2)), i2f(__ldg(t + 3)));
+    float3 e2 = f3(i2f(__ldg(t + 4)), i2f(__ldg(t + 5)), i2f(__ldg(t + 6)));
+    float3 pvec = cross3(dir, e2);
+    float det = dot3(e1, pvec);
+    if ((flags >> 8) & 1) {
+        if (det > -CCU_EPS && det < CCU_EPS) return nanf_();
+    } else if (det > -CCU_EPS) {
+        return nanf_();
+    }
+    float recip = 1.0f / det;
+    float3 o = f3(i2f(__ldg(t + 7)), i2f(__ldg(t + 8)), i2f(__ldg(t + 9)));
+    float3 tvec = origin - o;
+    float u = dot3(tvec, pvec) * recip;
+    if (u < 0 || u > 1) return nanf_();
+    float3 qvec = cross3(tvec, e1);
+    float v = dot3(dir, qvec) * recip;
+    if (v < 0 || (u + v) > 1) return nanf_();
+    float tt = dot3(e2, qvec) * recip;
+    if (tt > CCU_EPS && tt < distance) {
+        float w = 1.0f - u - v;
+        ou = (i2f(__ldg(t + 13)) * u + i2f(__ldg(t + 15)) * v) + i2f(__ldg(t + 17)) * w;
+        ov = (i2f(__ldg(t + 14)) * u + i2f(__ldg(t + 16)) * v) + i2f(__ldg(t + 18)) * w;
+        normal = f3(i2f(__ldg(t + 10)), i2f(__ldg(t + 11)), i2f(__ldg(t + 12)));
+        material = __ldg(t + 19);
+        return tt;
+    }
+    return nanf_();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// block.h:30-118
+// ------------------------------------------------------------------------------------------------------
+__device__ __noinline__ float intersect_model_block(const DScene &s, int model_type, int model_ptr, Record &rec,
+                                                    float3 norm_origin, float3 direction, float3 inv) {
+    float3 normal = f3(0, 0, 0);
+    float u = 0, v = 0;
+    bool hit = false;
+    float dist = inff_();
+    if (model_type == 2) {
+        int boxes = __ldg(s.aabb_models + model_ptr);
+        for (int i = 0; i < boxes; i++) {
+            int material = 0;
+            float t = textured_box(s.aabb_models + model_ptr + 1 + i * 13, dist, norm_origin, direction, inv, normal, u, v, material);
+            if (!is_nan(t) && material_sample(s, material, rec, u, v)) { rec.normal = normal; dist = t; hit = true; }
+        }
+    } else {
+        int quads = __ldg(s.quad_models + model_ptr);
+        for (int i = 0; i < quads; i++) {
+            const int *q = s.quad_models + model_ptr + 1 + i * 15;
+            float t = quad_hit(q, dist, norm_origin, direction, normal, u, v);
+            if (!is_nan(t) && material_sample(s, __ldg(q + 13), rec, u, v)) { rec.normal = normal; dist = t; hit = true; }
+        }
+    }
+    return hit ? dist : nanf_();
+}
+
+__device__ __forceinline__ float intersect_block(const DScene &s, int block, int bx, int by, int bz, Record &rec, float3 pos,
+                                                 float3 direction, float3 inv) {
+    if (block == CCU_ANY_TYPE) return nanf_();
+    if (block < 0 || block + 1 >= s.block_palette_len) return nanf_();   // out-of-palette leaf (undefined in the reference)
+    int model_type = __ldg(s.block_palette + block), model_ptr = __ldg(s.block_palette + block + 1);
+    float3 norm_origin = (pos - direction * CCU_OFFSET) - f3((float)bx, (float)by, (float)bz);
+    if (model_type == 1) {
+        Box unit = {0, 1, 0, 1, 0, 1};
+        float3 normal = f3(0, 0, 0);
+        float u = 0, v = 0;
+        // the marched position stands in for the direction here, as in block.h:52
+        float dist = box_full<false>(unit, norm_origin, pos, inv, normal, u, v);
+        if (is_nan(dist)) return nanf_();
+        rec.normal = normal;
+        return material_sample(s, model_ptr, rec, u, v) ? dist - CCU_OFFSET : nanf_();
+    }
+    if (model_type == 2 || model_type == 3) return intersect_model_block(s, model_type, model_ptr, rec, norm_origin, direction, inv);
+    return nanf_();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// octree.h:41-109.  find_leaf returns what the reference's root descent (octree.h:81-88) returns for the
+// voxel (bx,by,bz): the leaf word, the leaf level and the leaf's index in treeData.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_leaf(const DScene &s, int bx, int by, int bz, int &level, int &node) {
+    int lvl = s.depth;
+    int idx = 0;
+    int data = __ldg(s.tree);
+    while (data > 0) {
+        lvl--;
+        idx = data + ((((bx >> lvl) & 1) << 2) | (((by >> lvl) & 1) << 1) | ((bz >> lvl) & 1));
+        data = __ldg(s.tree + idx);
+    }
+    level = lvl;
+    node = idx;
+    return -data;
+}
+
+__device__ __forceinline__ bool octree_intersect(const DScene &s, float3 origin, float3 direction, Record &rec, HitInfo &hi) {
+    const int depth = s.depth;
+    float dist_march = 0;
+    float3 inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+    float3 offset_d = direction * CCU_OFFSET;
+    {
+        int lx = f2i(floorf(origin.x)) >> depth, ly = f2i(floorf(origin.y)) >> depth, lz = f2i(floorf(origin.z)) >> depth;
+        if ((lx | ly | lz) != 0) {
+            float size = (float)(1 << depth);
+            Box cube = {0, size, 0, size, 0, size};
+            float dist = box_entry(cube, origin, inv);
+            if (is_nan(dist) || dist < 0) return false;
+            dist_march += dist + CCU_OFFSET;
+        }
+    }
+    for (int i = 0; i < s.draw_depth; i++) {
+        if (dist_march > rec.distance) return false;
+        float3 pos = origin + direction * dist_march;
+        float3 q = pos + offset_d;
+        int bx = f2i(floorf(q.x)), by = f2i(floorf(q.y)), bz = f2i(floorf(q.z));
+        if (((bx >> depth) | (by >> depth) | (bz >> depth)) != 0) return false;
+        int level, node;
+        int data = find_leaf(s, bx, by, bz, level, node);
+        if (data != 0) {
+            float dist = intersect_block(s, data, bx, by, bz, rec, pos, direction, inv);
+            if (!is_nan(dist)) {
+                rec.distance = dist_march + dist;
+                rec.material = data;
+                hi.node = node;
+                hi.kind = 1;
+                return true;
+            }
+        }
+        int lx = bx >> level, ly = by >> level, lz = bz >> level;
+        Box leaf = {(float)(lx << level), (float)((lx + 1) << level), (float)(ly << level), (float)((ly + 1) << level),
+                    (float)(lz << level), (float)((lz + 1) << level)};
+        dist_march += box_exit(leaf, q, inv) + CCU_OFFSET;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// bvh.h:22-113
+// ------------------------------------------------------------------------------------------------------
+__device__ __noinline__ bool bvh_intersect(const DScene &s, const int *__restrict__ bvh, float3 origin, float3 direction,
+                                           Record &rec, HitInfo &hi, int kind) {
+    bool hit = false;
+    int to_visit = 0, current = 0;
+    int stack[64];
+    float3 inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+    for (;;) {
+        int head = __ldg(bvh + current);
+        if (head <= 0) {
+            int prim = -head;
+            int num = __ldg(s.trigs + prim);
+            for (int i = 0; i < num; i++) {
+                float3 normal;
+                float u, v;
+                int material;
+                float dist = triangle_hit(s.trigs + prim + 1 + 20 * i, rec.distance, origin, direction, normal, u, v, material);
+                if (!is_nan(dist) && material_sample(s, material, rec, u, v)) {
+                    rec.normal = normal;      // record.material keeps its octree value (bvh.h:59-65)
+                    rec.distance = dist;
+                    hit = true;
+                    hi.kind = kind;
+                    hi.node = -1;
+                }
+            }
+            if (to_visit == 0) break;
+            current = stack[--to_visit];
+        } else {
+            int second = head;
+            const int *n1 = bvh + current + 7;
+            const int *n2 = bvh + second;
+            Box b1 = {i2f(__ldg(n1 + 1)), i2f(__ldg(n1 + 2)), i2f(__ldg(n1 + 3)), i2f(__ldg(n1 + 4)), i2f(__ldg(n1 + 5)), i2f(__ldg(n1 + 6))};
+            Box b2 = {i2f(__ldg(n2 + 1)), i2f(__ldg(n2 + 2)), i2f(__ldg(n2 + 3)), i2f(__ldg(n2 + 4)), i2f(__ldg(n2 + 5)), i2f(__ldg(n2 + 6))};
+            float t1 = box_entry(b1, origin, inv);
+            float t2 = box_entry(b2, origin, inv);
+            bool miss1 = is_nan(t1) || t1 > rec.distance;
+            bool miss2 = is_nan(t2) || t2 > rec.distance;
+            if (miss1) {
+                if (miss2) {
+                    if (to_visit == 0) break;
+                    current = stack[--to_visit];
+                } else {
+                    current = second;
+                }
+            } else if (miss2) {
+                current += 7;
+            } else if (t1 < t2) {
+                stack[to_visit++] = second;
+                current += 7;
+            } else {
+                stack[to_visit++] = current + 7;
+                current = second;
+            }
+        }
+    }
+    return hit;
+}
+
+// kernel.h:14-24
+__device__ __forceinline__ bool closest_intersect(const DScene &s, float3 origin, float3 direction, Record &rec, HitInfo &hi) {
+    bool hit = octree_intersect(s, origin, direction, rec, hi);
+    if (!s.world_bvh_empty) hit |= bvh_intersect(s, s.world_bvh, origin, direction, rec, hi, 2);
+    if (!s.actor_bvh_empty) hit |= bvh_intersect(s, s.actor_bvh, origin, direction, rec, hi, 3);
+    if (hit) rec.point = origin + direction * (rec.distance - CCU_OFFSET);
+    return hit;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// sky.h / kernel.h shading
+// ------------------------------------------------------------------------------------------------------
+// sky.h:97-106 + sky.h:42-66, then the accumulation of kernel.h:26-31
+__device__ __forceinline__ float3 sky_radiance(const DScene &s, float3 d) {
+    float theta = dm_atan2(d.z, d.x);
+    theta /= CCU_PI_F * 2;
+    theta = fmodf(fmodf(theta, 1.0f) + 1.0f, 1.0f);
+    float phi = (dm_asin(fminf(fmaxf(d.y, -1.0f), 1.0f)) + CCU_PI_2_F) * CCU_INV_PI_F;
+    float4 sky = sky_read(s, theta, phi);
+    float3 col = f3(sky.x * s.sky_intensity, sky.y * s.sky_intensity, sky.z * s.sky_intensity);
+    if ((s.sun_flags & 1) && !(dot3(d, s.sw) < 0.5f)) {
+        const float radius = 0.03f;
+        const float width = radius * 4;
+        const float width2 = width * 2;
+        float a = CCU_PI_2_F - dm_acos(dot3(d, s.su)) + width;
+        if (a >= 0 && a < width2) {
+            float b = CCU_PI_2_F - dm_acos(dot3(d, s.sv)) + width;
+            if (b >= 0 && b < width2) {
+                float4 sc = atlas_read_uv(s, a / width2, b / width2, s.sun_tex, s.sun_tex_size);
+                col.x += sc.x * s.sun_intensity;
+                col.y += sc.y * s.sun_intensity;
+                col.z += sc.z * s.sun_intensity;
+            }
+        }
+    }
+    return col;
+}
+
+struct PathState {
+    float3 origin, direction;
+    float3 color, throughput;
+    uint32_t rng;
+    int ray_depth;
+};
+
+// camera.h:8-32 + rayTracer.cl:55-91 (NORMALIZE = preview variant, rayTracer.cl:186)
+template <bool NORMALIZE>
+__device__ __forceinline__ void camera_ray(const DScene &s, int gid, uint32_t &rng, float3 &origin, float3 &direction) {
+    if (s.projector_type != -1) {
+        float half_width = (float)(s.width / (2.0 * s.height));
+        float inv_height = (float)(1.0 / s.height);
+        float x = -half_width + ((float)(gid % s.width) + rng_float(rng)) * inv_height;
+        float y = (float)(-0.5 + (double)(((float)(gid / s.width) + rng_float(rng)) * inv_height));
+        float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
+        if (s.projector_type == 0) {
+            float aperture = s.cam[12], subject_distance = s.cam[13], fov_tan = s.cam[14];
+            d = f3(fov_tan * x, fov_tan * y, 1.0f);
+            if (aperture > 0) {
+                d = d * (subject_distance / d.z);
+                float r = sqrtf(rng_float(rng)) * aperture;
+                float theta = rng_float(rng) * CCU_PI_F * 2.0f;
+                float sn, cs;
+                dm_sincos(theta, sn, cs);
+                float rx = cs * r, ry = sn * r;
+                d = d - f3(rx, ry, 0);
+                o = o + f3(rx, ry, 0);
+            }
+        }
+        if (NORMALIZE) d = normalize3(d);
+        float3 m1 = f3(s.cam[3], s.cam[4], s.cam[5]), m2 = f3(s.cam[6], s.cam[7], s.cam[8]), m3 = f3(s.cam[9], s.cam[10], s.cam[11]);
+        direction = f3(dot3(m1, d), dot3(m2, d), dot3(m3, d));
+        origin = f3(dot3(m1, o), dot3(m2, o), dot3(m3, o)) + f3(s.cam[0], s.cam[1], s.cam[2]);
+    } else {
+        const float *r = s.rays + (size_t)gid * 6;
+        origin = f3(__ldg(r), __ldg(r + 1), __ldg(r + 2));
+        direction = f3(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
+    }
+}
+
+// one path sample for pixel gid: rayTracer.cl:40-107 (+ kernel.h:33-98, sky.h:68-93)
+__device__ __forceinline__ float3 sample_pixel(const DScene &s, int gid, int seed) {
+    PathState p;
+    p.color = f3(0, 0, 0);
+    p.throughput = f3(1, 1, 1);
+    p.ray_depth = 0;
+    p.rng = (uint32_t)seed + (uint32_t)gid;
+    rng_next(p.rng);
+    camera_ray<false>(s, gid, p.rng, p.origin, p.direction);
+    Record rec;
+    rec.distance = inff_();
+    rec.material = 0;
+    rec.normal = f3(0, 0, 0);
+    rec.point = f3(0, 0, 0);
+    rec.color = make_float4(0, 0, 0, 0);
+    rec.emittance = 0;
+    HitInfo hi = {-1, 0};
+    for (;;) {
+        if (!closest_intersect(s, p.origin, p.direction, rec, hi)) {
+            // miss: emittance = 1, sky (+ sun disc) added through the throughput (rayTracer.cl:95-97, kernel.h:26-31)
+            float3 sky = sky_radiance(s, p.direction);
+            p.color = p.color + (sky * p.throughput) * 1.0f;
+            break;
+        }
+        // kernel.h:33-44
+        p.origin = rec.point;
+        float3 col = f3(rec.color.x, rec.color.y, rec.color.z);
+        p.throughput = p.throughput * col;
+        p.color = p.color + (col * (rec.emittance * s.emitter_scale)) * p.throughput;
+        // sun sampling + shadow ray (sky.h:68-93, rayTracer.cl:101-106)
+        if (s.sun_flags & 1) {
+            float x1 = rng_float(p.rng);
+            float x2 = rng_float(p.rng);
+            float cos_a = 1 - x1 + x1 * s.sun_radius_cos;
+            float sin_a = sqrtf(1 - cos_a * cos_a);
+            float phi = 2 * CCU_PI_F * x2;
+            float sn, cs;
+            dm_sincos(phi, sn, cs);
+            float3 u = s.su * (cs * sin_a);
+            float3 v = s.sv * (sn * sin_a);
+            float3 w = s.sw * cos_a;
+            float3 d = normalize3((u * v) + w);      // component-wise product, as the reference
+            p.direction = d;
+            float shadow_emittance = fabsf(dot3(d, rec.normal));
+            Record sh = rec;                          // keeps the surface hit's distance as the ray limit
+            HitInfo shi;
+            if (!closest_intersect(s, p.origin, d, sh, shi)) {
+                float3 sky = sky_radiance(s, d);
+                p.color = p.color + (sky * p.throughput) * shadow_emittance;
+            }
+        }
+        // kernel.h:46-98 diffuse bounce
+        {
+            float x1 = rng_float(p.rng);
+            float x2 = rng_float(p.rng);
+            float r = sqrtf(x1);
+            float theta = 2 * CCU_PI_F * x2;
+            float sn, cs;
+            dm_sincos(theta, sn, cs);
+            float tx = r * cs, ty = r * sn;
+            float tz = sqrtf(1 - x1);
+            float3 n = rec.normal;
+            float xx, xy, xz = 0;
+            if ((double)fabsf(n.x) > 0.1) { xx = 0; xy = 1; } else { xx = 1; xy = 0; }
+            float ux = xy * n.z - xz * n.y;
+            float uy = xz * n.x - xx * n.z;
+            float uz = xx * n.y - xy * n.x;
+            r = 1 / sqrtf((ux * ux + uy * uy) + uz * uz);
+            ux *= r; uy *= r; uz *= r;
+            float vx = uy * n.z - uz * n.y;
+            float vy = uz * n.x - ux * n.z;
+            float vz = ux * n.y - uy * n.x;
+            p.direction = f3((ux * tx + vx * ty) + n.x * tz, (uy * tx + vy * ty) + n.y * tz, (uz * tx + vz * ty) + n.z * tz);
+            p.origin = rec.point + p.direction * CCU_OFFSET;
+            p.ray_depth += 1;
+            rec.distance = inff_();
+            if (!(p.ray_depth < s.max_depth)) break;
+        }
+    }
+    return p.color;
+}
+
+}  // namespace ccu

@@ -1,0 +1,103 @@
+// ccu_math.cuh - fp32 vector helpers and the deterministic transcendental set ("detmath").
+//
+// Arithmetic contract: every fp32 operation is one IEEE-754 round-to-nearest operation in the
+// order written.  The translation unit is compiled with -fmad=false (no contraction), default
+// -prec-div=true -prec-sqrt=true -ftz=false.  sin/cos/atan2/asin/acos are fixed polynomial kernels built
+// from +,-,*,/,sqrt,floor only, so the full path - not just the integer first-hit buffers - reproduces
+// bit-for-bit on any IEEE machine.  (The reference calls the OpenCL builtins cos/sin/atan2/asin/acos,
+// sky.h:26-37,51-53,80-82,99-103, kernel.h:57-59, camera.h:26-27, whose results are implementation
+// defined to a few ulp; detmath stays within 2 ulp of them on the ranges used - tests/test_math.py.)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ccu {
+
+#define CCU_EPS 0.000005f    // constants.h:4
+#define CCU_OFFSET 0.0001f   // constants.h:5
+#define CCU_PI_F 3.14159274101257f
+#define CCU_PI_2_F 1.57079637050629f
+#define CCU_INV_PI_F 0.318309886183791f
+
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) {
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float3 normalize3(float3 a) {
+    float inv = 1.0f / sqrtf(dot3(a, a));
+    return a * inv;
+}
+// cvt.rzi.s32.f32: toward zero, saturating, NaN -> 0
+__device__ __forceinline__ int f2i(float f) { return __float2int_rz(f); }
+__device__ __forceinline__ float i2f(int bits) { return __int_as_float(bits); }
+__device__ __forceinline__ bool is_nan(float f) { return f != f; }
+__device__ __forceinline__ float nanf_() { return __int_as_float(0x7fc00000); }
+__device__ __forceinline__ float inff_() { return __int_as_float(0x7f800000); }
+
+__device__ __forceinline__ void dm_sincos(float x, float &s, float &c) {
+    float kf = floorf(x * 0.636619772f + 0.5f);
+    float r = x - kf * 1.5703125f;
+    r = r - kf * 4.837512969970703125e-4f;
+    r = r - kf * 7.54978995489188216e-8f;
+    int k = f2i(kf) & 3;
+    float z = r * r;
+    float sp = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+    float cp = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+    float ss = (k & 1) ? cp : sp;
+    float cc = (k & 1) ? sp : cp;
+    s = (k & 2) ? -ss : ss;
+    c = ((k + 1) & 2) ? -cc : cc;
+}
+__device__ __forceinline__ float dm_cos(float x) { float s, c; dm_sincos(x, s, c); return c; }
+__device__ __forceinline__ float dm_sin(float x) { float s, c; dm_sincos(x, s, c); return s; }
+
+__device__ __forceinline__ float dm_atan(float t) {
+    float sign = 1.0f, y0 = 0.0f;
+    if (t < 0.0f) { t = -t; sign = -1.0f; }
+    if (t > 2.414213562373095f) { y0 = 1.5707963267948966f; t = -(1.0f / t); }
+    else if (t > 0.4142135623730950f) { y0 = 0.7853981633974483f; t = (t - 1.0f) / (t + 1.0f); }
+    float z = t * t;
+    float p = (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * t + t;
+    return sign * (y0 + p);
+}
+__device__ __forceinline__ float dm_atan2(float y, float x) {
+    if (x != x || y != y) return nanf_();
+    if (x > 0.0f) return dm_atan(y / x);
+    if (x < 0.0f) return (y >= 0.0f) ? dm_atan(y / x) + 3.14159265358979f : dm_atan(y / x) - 3.14159265358979f;
+    if (y > 0.0f) return 1.5707963267948966f;
+    if (y < 0.0f) return -1.5707963267948966f;
+    return 0.0f;
+}
+__device__ __forceinline__ float dm_asin(float x) {
+    float a = fabsf(x);
+    if (a > 1.0f) return nanf_();
+    bool big = a > 0.5f;
+    float z, t;
+    if (big) { z = 0.5f * (1.0f - a); t = sqrtf(z); } else { t = a; z = t * t; }
+    float p = ((((4.2163199048e-2f * z + 2.4181311049e-2f) * z + 4.5470025998e-2f) * z + 7.4953002686e-2f) * z + 1.6666752422e-1f) * z * t + t;
+    if (big) p = 1.5707963267948966f - (p + p);
+    return x < 0.0f ? -p : p;
+}
+__device__ __forceinline__ float dm_acos(float x) {
+    if (fabsf(x) > 1.0f) return nanf_();
+    if (x < -0.5f) return 3.14159265358979f - 2.0f * dm_asin(sqrtf(0.5f * (1.0f + x)));
+    if (x > 0.5f) return 2.0f * dm_asin(sqrtf(0.5f * (1.0f - x)));
+    return 1.5707963267948966f - dm_asin(x);
+}
+
+// PCG hash RNG: randomness.h:6-17
+__device__ __forceinline__ uint32_t rng_next(uint32_t &state) {
+    uint32_t s = state * 47796405u + 2891336453u;
+    s = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
+    s = (s >> 22u) ^ s;
+    state = s;
+    return s;
+}
+__device__ __forceinline__ float rng_float(uint32_t &state) { return (float)(rng_next(state) >> 8) / 16777216.0f; }
+
+}  // namespace ccu

@@ -1,0 +1,823 @@
+// chunkycu.cu - kernels and the C ABI (include/chunkycu.h) of libchunkycu.so.  sm_100a only.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/chunkycu.h"
+#include "ccu_device.cuh"
+
+using namespace ccu;
+
+// ======================================================================================================
+// kernels
+// ======================================================================================================
+
+// Sun_new (sky.h:19-40) once per scene, on the device so it uses the device's arithmetic.
+__global__ void k_sun_setup(const int *sun_words, float *out /* su sv sw radius_cos : 10 floats */) {
+    float phi = i2f(sun_words[4]), theta = i2f(sun_words[5]);
+    float r = fabsf(dm_cos(phi));
+    float3 sw = f3(dm_cos(theta) * r, dm_sin(phi), dm_sin(theta) * r);
+    float3 su = (fabsf(sw.x) > 0.1f) ? f3(0, 1, 0) : f3(1, 0, 0);
+    float3 sv = normalize3(cross3(sw, su));
+    su = cross3(sv, sw);
+    out[0] = su.x; out[1] = su.y; out[2] = su.z;
+    out[3] = sv.x; out[4] = sv.y; out[5] = sv.z;
+    out[6] = sw.x; out[7] = sw.y; out[8] = sw.z;
+    out[9] = dm_cos(0.03f);
+}
+
+// Thread-per-pixel path tracer: all passes of the batch in one launch, the running mean of
+// rayTracer.cl:109-112 carried in registers between passes (identical arithmetic, no memory round trip).
+__global__ void __launch_bounds__(128) k_render_mega(const __grid_constant__ DScene s, const int *__restrict__ seeds, int n_passes,
+                                                     int start_spp, float *__restrict__ res, int n_pixels) {
+    for (int gid = blockIdx.x * blockDim.x + threadIdx.x; gid < n_pixels; gid += gridDim.x * blockDim.x) {
+        float *px = res + (size_t)gid * 3;
+        float3 buf = f3(px[0], px[1], px[2]);
+        for (int pass = 0; pass < n_passes; pass++) {
+            float3 col = sample_pixel(s, gid, __ldg(seeds + pass));
+            int spp = start_spp + pass;
+            float fs = (float)spp, fs1 = (float)(spp + 1);
+            buf.x = (buf.x * fs + col.x) / fs1;
+            buf.y = (buf.y * fs + col.y) / fs1;
+            buf.z = (buf.z * fs + col.z) / fs1;
+        }
+        px[0] = buf.x; px[1] = buf.y; px[2] = buf.z;
+    }
+}
+
+__device__ __forceinline__ int face_of(float3 n) {
+    if (n.x == -1 && n.y == 0 && n.z == 0) return 0;
+    if (n.x == 1 && n.y == 0 && n.z == 0) return 1;
+    if (n.x == 0 && n.y == -1 && n.z == 0) return 2;
+    if (n.x == 0 && n.y == 1 && n.z == 0) return 3;
+    if (n.x == 0 && n.y == 0 && n.z == -1) return 4;
+    if (n.x == 0 && n.y == 0 && n.z == 1) return 5;
+    return 6;
+}
+
+__global__ void __launch_bounds__(128) k_first_hit(const __grid_constant__ DScene s, int seed, int n_pixels, int *block, int *face, int *node,
+                                                   int *kind, float *t, float *normal, float *color) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_pixels) return;
+    uint32_t rng = (uint32_t)seed + (uint32_t)gid;
+    rng_next(rng);
+    float3 o, d;
+    camera_ray<false>(s, gid, rng, o, d);
+    Record rec;
+    rec.distance = inff_(); rec.material = 0; rec.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
+    rec.color = make_float4(0, 0, 0, 0); rec.emittance = 0;
+    HitInfo hi = {-1, 0};
+    bool hit = closest_intersect(s, o, d, rec, hi);
+    if (block) block[gid] = hit ? rec.material : 0;
+    if (face) face[gid] = hit ? face_of(rec.normal) : 6;
+    if (node) node[gid] = hit ? hi.node : -1;
+    if (kind) kind[gid] = hit ? hi.kind : 0;
+    if (t) t[gid] = hit ? rec.distance : inff_();
+    if (normal) {
+        normal[gid * 3 + 0] = hit ? rec.normal.x : 0.0f;
+        normal[gid * 3 + 1] = hit ? rec.normal.y : 0.0f;
+        normal[gid * 3 + 2] = hit ? rec.normal.z : 0.0f;
+    }
+    if (color) {
+        float4 c = hit ? rec.color : make_float4(0, 0, 0, 0);
+        reinterpret_cast<float4 *>(color)[gid] = c;
+    }
+}
+
+// rayTracer.cl:141-216
+__global__ void __launch_bounds__(128) k_preview(const __grid_constant__ DScene s, int n_pixels, int *res) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_pixels) return;
+    int W = s.width, H = s.height;
+    int px = gid % W, py = gid / W;
+    if ((px == W / 2 && (py >= H / 2 - 5 && py <= H / 2 + 5)) || (py == H / 2 && (px >= W / 2 - 5 && px <= W / 2 + 5))) {
+        res[gid] = (int)0xFFFFFFFFu;
+        return;
+    }
+    uint32_t rng = 0;
+    rng_next(rng);
+    float3 o, d;
+    camera_ray<true>(s, gid, rng, o, d);
+    Record rec;
+    rec.distance = inff_(); rec.material = 0; rec.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
+    rec.color = make_float4(0, 0, 0, 0); rec.emittance = 0;
+    HitInfo hi = {-1, 0};
+    float3 c;
+    if (closest_intersect(s, o, d, rec, hi)) {
+        float shading = dot3(rec.normal, f3(0.25f, 0.866f, 0.433f));
+        shading = fmaxf(0.3f, shading);
+        c = f3(rec.color.x * shading, rec.color.y * shading, rec.color.z * shading);
+    } else {
+        c = sky_radiance(s, d);
+    }
+    float v[3] = {c.x, c.y, c.z};
+    int rgb[3];
+    for (int i = 0; i < 3; i++) {
+        float q = sqrtf(v[i]) * 255.0f;
+        q = fminf(fmaxf(q, 0.0f), 255.0f);
+        rgb[i] = f2i(floorf(q));
+    }
+    res[gid] = (int)(0xFF000000u | ((uint32_t)rgb[0] << 16) | ((uint32_t)rgb[1] << 8) | (uint32_t)rgb[2]);
+}
+
+__global__ void k_scale(float *buf, float factor, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] *= factor;
+}
+
+// Re-tile a row-major RGBA8 rectangle into the tile-linear atlas (16x16 texel tiles contiguous = 1 KiB each).
+__global__ void k_atlas_write(uchar4 *atlas, int tiles_x, int tiles_y, int x0, int y0, int layer, int w, int h, const uchar4 *src) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    int x = x0 + i % w, y = y0 + i / w;
+    size_t tile = ((size_t)layer * tiles_y + (y >> 4)) * tiles_x + (x >> 4);
+    atlas[tile * 256 + ((y & 15) << 4) + (x & 15)] = src[i];
+}
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                                     \
+    do {                                                                                                             \
+        cudaError_t e_ = (call);                                                                                     \
+        if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? CCU_ENOMEM : CCU_ECUDA, "%s: %s (%s:%d)", #call, \
+                                           cudaGetErrorString(e_), __FILE__, __LINE__);                              \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t upload(const T *host, size_t count, cudaStream_t st) {
+        release();
+        n = count;
+        size_t alloc = std::max<size_t>(count, 4);   // zero-length arrays become a zero word (ClIntBuffer.java:15-18)
+        cudaError_t e = cudaMalloc(&p, alloc * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        e = cudaMemsetAsync(p, 0, alloc * sizeof(T), st);
+        if (e != cudaSuccess) return e;
+        if (count) e = cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+        return cudaStreamSynchronize(st);   // host memory is not retained past the call
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return p ? std::max<size_t>(n, 4) * sizeof(T) : 0; }
+};
+
+struct ccu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+    int sm_count = 0;
+
+    // scene
+    DevBuf<int> tree, block_palette, quad_models, aabb_models, mat_palette, trigs, world_bvh, actor_bvh, sun_words;
+    std::vector<int> world_head, actor_head;    // first node of each BVH for the emptiness probe
+    DevBuf<uchar4> atlas, sky;
+    int atlas_w = 0, atlas_h = 0, atlas_layers = 0;
+    int depth = 0, sky_res = 0;
+    float sky_intensity = 0;
+    int sun_host[6] = {0, 0, 0, 0, 0, 0};
+    bool have_sun = false;
+    bool committed = false;
+    DevBuf<float> sun_basis;
+
+    // camera
+    int projector_type = 0;
+    float cam[15] = {0};
+    DevBuf<float> rays;
+    bool have_camera = false;
+
+    // render target
+    int width = 0, height = 0;
+    float *accum = nullptr;      // running mean float[3*W*H]
+    float *pinned = nullptr;     // host staging float[3*W*H]
+    int *seeds_dev = nullptr;
+    int seeds_cap = 0;
+    int window_spp = 0;
+    ccu_render_params params = {256, 5, 13.0f, 0};
+
+    float last_ms = 0;
+    bool timing_pending = false;
+    int64_t launches = 0;
+
+    DScene scene{};
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+bool bvh_is_empty(const std::vector<int> &head) {   // bvh.h:23-32
+    if (head.size() < 7 || head[0] != 0) return head.size() < 7;
+    for (int i = 1; i < 7; i++) {
+        float f;
+        memcpy(&f, &head[i], 4);
+        if (!std::isnan(f)) return false;
+    }
+    return true;
+}
+
+int fill_scene(ccu_ctx *c) {
+    DScene &s = c->scene;
+    s.tree = c->tree.p;
+    s.depth = c->depth;
+    s.block_palette = c->block_palette.p;
+    s.block_palette_len = (int)c->block_palette.n;
+    s.quad_models = c->quad_models.p;
+    s.aabb_models = c->aabb_models.p;
+    s.mat_palette = c->mat_palette.p;
+    s.world_bvh = c->world_bvh.p;
+    s.actor_bvh = c->actor_bvh.p;
+    s.trigs = c->trigs.p;
+    s.world_bvh_empty = bvh_is_empty(c->world_head);
+    s.actor_bvh_empty = bvh_is_empty(c->actor_head);
+    s.atlas = c->atlas.p;
+    s.atlas_w = c->atlas_w; s.atlas_h = c->atlas_h; s.atlas_layers = c->atlas_layers;
+    s.atlas_tiles_x = (c->atlas_w + 15) / 16; s.atlas_tiles_y = (c->atlas_h + 15) / 16;
+    s.sky = c->sky.p;
+    s.sky_res = c->sky_res;
+    s.sky_intensity = c->sky_intensity;
+    s.sun_flags = c->sun_host[0]; s.sun_tex_size = c->sun_host[1]; s.sun_tex = c->sun_host[2];
+    memcpy(&s.sun_intensity, &c->sun_host[3], 4);
+    s.projector_type = c->projector_type;
+    memcpy(s.cam, c->cam, sizeof s.cam);
+    s.rays = c->rays.p;
+    s.width = c->width; s.height = c->height;
+    s.draw_depth = c->params.draw_depth; s.max_depth = c->params.max_depth; s.emitter_scale = c->params.emitter_scale;
+    return CCU_OK;
+}
+
+int upload_words(ccu_ctx *c, DevBuf<int> &dst, const int32_t *words, int64_t n, const char *what) {
+    if (!c) return fail(CCU_EINVAL, "%s: null context", what);
+    if (n < 0 || (n > 0 && !words)) return fail(CCU_EINVAL, "%s: bad array (n=%lld)", what, (long long)n);
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    c->committed = false;
+    CU(dst.upload(words, (size_t)n, c->stream));
+    return CCU_OK;
+}
+
+void stop_timer(ccu_ctx *c) {
+    if (c->timing_pending) {
+        cudaEventSynchronize(c->ev1);
+        cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+        c->timing_pending = false;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *ccu_last_error(void) { return g_err.c_str(); }
+const char *ccu_version(void) { return "chunkycu 0.1 (sm_100a)"; }
+
+int ccu_device_count(int *count) {
+    if (!count) return fail(CCU_EINVAL, "ccu_device_count: null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(CCU_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return CCU_OK;
+}
+
+int ccu_device_info(int index, char *name, int name_len, int *sm_count, int *clock_khz, uint64_t *mem_bytes) {
+    int n = 0;
+    int rc = ccu_device_count(&n);
+    if (rc != CCU_OK) return rc;
+    if (index < 0 || index >= n) return fail(CCU_EINVAL, "device index %d out of range [0,%d)", index, n);
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, index));
+    if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", p.name);
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (clock_khz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, index);
+        *clock_khz = khz;
+    }
+    if (mem_bytes) *mem_bytes = (uint64_t)p.totalGlobalMem;
+    return CCU_OK;
+}
+
+int ccu_ctx_create(int device_index, ccu_ctx **out) {
+    if (!out) return fail(CCU_EINVAL, "ccu_ctx_create: null out");
+    *out = nullptr;
+    int n = 0;
+    int rc = ccu_device_count(&n);
+    if (rc != CCU_OK) return rc;
+    if (n == 0) return fail(CCU_ENODEVICE, "no CUDA device");
+    if (device_index < 0 || device_index >= n) return fail(CCU_EINVAL, "device index %d out of range [0,%d)", device_index, n);
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device_index));
+    if (p.major != 10) return fail(CCU_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device_index, p.major, p.minor);
+    ccu_ctx *c = new ccu_ctx();
+    c->device = device_index;
+    c->sm_count = p.multiProcessorCount;
+    DeviceGuard g(device_index);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(CCU_ECUDA, "context setup: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return CCU_OK;
+}
+
+int ccu_render_end(ccu_ctx *c);
+
+int ccu_ctx_destroy(ccu_ctx *c) {
+    if (!c) return CCU_OK;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        DeviceGuard g(c->device);
+        cudaStreamSynchronize(c->stream);
+        c->tree.release(); c->block_palette.release(); c->quad_models.release(); c->aabb_models.release();
+        c->mat_palette.release(); c->trigs.release(); c->world_bvh.release(); c->actor_bvh.release();
+        c->sun_words.release(); c->atlas.release(); c->sky.release(); c->rays.release(); c->sun_basis.release();
+        if (c->accum) cudaFree(c->accum);
+        if (c->pinned) cudaFreeHost(c->pinned);
+        if (c->seeds_dev) cudaFree(c->seeds_dev);
+        cudaEventDestroy(c->ev0);
+        cudaEventDestroy(c->ev1);
+        cudaStreamDestroy(c->stream);
+    }
+    delete c;
+    return CCU_OK;
+}
+
+int ccu_scene_begin(ccu_ctx *c) {
+    if (!c) return fail(CCU_EINVAL, "ccu_scene_begin: null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->committed = false;
+    return CCU_OK;
+}
+
+int ccu_scene_set_octree(ccu_ctx *c, const int32_t *tree, int64_t n, int32_t depth) {
+    if (depth < 0 || depth > 30) return fail(CCU_EINVAL, "octree depth %d out of range", depth);
+    if (n < 1) return fail(CCU_EINVAL, "octree needs at least the root word");
+    int rc = upload_words(c, c->tree, tree, n, "ccu_scene_set_octree");
+    if (rc == CCU_OK) c->depth = depth;
+    return rc;
+}
+int ccu_scene_set_block_palette(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->block_palette, w, n, "ccu_scene_set_block_palette"); }
+int ccu_scene_set_quad_models(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->quad_models, w, n, "ccu_scene_set_quad_models"); }
+int ccu_scene_set_aabb_models(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->aabb_models, w, n, "ccu_scene_set_aabb_models"); }
+int ccu_scene_set_material_palette(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->mat_palette, w, n, "ccu_scene_set_material_palette"); }
+int ccu_scene_set_triangles(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->trigs, w, n, "ccu_scene_set_triangles"); }
+int ccu_scene_set_world_bvh(ccu_ctx *c, const int32_t *w, int64_t n) {
+    int rc = upload_words(c, c->world_bvh, w, n, "ccu_scene_set_world_bvh");
+    if (rc == CCU_OK) c->world_head.assign(w, w + std::min<int64_t>(n, 7));
+    return rc;
+}
+int ccu_scene_set_actor_bvh(ccu_ctx *c, const int32_t *w, int64_t n) {
+    int rc = upload_words(c, c->actor_bvh, w, n, "ccu_scene_set_actor_bvh");
+    if (rc == CCU_OK) c->actor_head.assign(w, w + std::min<int64_t>(n, 7));
+    return rc;
+}
+
+int ccu_scene_atlas_create(ccu_ctx *c, int32_t width, int32_t height, int32_t layers) {
+    if (!c) return fail(CCU_EINVAL, "ccu_scene_atlas_create: null context");
+    if (width <= 0 || height <= 0 || layers <= 0 || width > 16384 || height > 16384) return fail(CCU_EINVAL, "bad atlas extents %dx%dx%d", width, height, layers);
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    c->committed = false;
+    c->atlas.release();
+    size_t tiles = (size_t)((width + 15) / 16) * ((height + 15) / 16) * layers;
+    c->atlas.n = tiles * 256;
+    CU(cudaMalloc(&c->atlas.p, c->atlas.n * sizeof(uchar4)));
+    CU(cudaMemsetAsync(c->atlas.p, 0, c->atlas.n * sizeof(uchar4), c->stream));
+    c->atlas_w = width; c->atlas_h = height; c->atlas_layers = layers;
+    return CCU_OK;
+}
+
+int ccu_scene_atlas_write(ccu_ctx *c, int32_t x, int32_t y, int32_t layer, int32_t w, int32_t h, const uint8_t *rgba) {
+    if (!c) return fail(CCU_EINVAL, "ccu_scene_atlas_write: null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->atlas.p) return fail(CCU_ESTATE, "atlas not created");
+    if (!rgba || w <= 0 || h <= 0 || x < 0 || y < 0 || layer < 0 || x + w > c->atlas_w || y + h > c->atlas_h || layer >= c->atlas_layers)
+        return fail(CCU_EINVAL, "atlas write %dx%d at (%d,%d,%d) outside %dx%dx%d", w, h, x, y, layer, c->atlas_w, c->atlas_h, c->atlas_layers);
+    DeviceGuard g(c->device);
+    c->committed = false;
+    uchar4 *tmp = nullptr;
+    size_t bytes = (size_t)w * h * 4;
+    CU(cudaMalloc(&tmp, bytes));
+    cudaError_t e = cudaMemcpyAsync(tmp, rgba, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        int n = w * h;
+        k_atlas_write<<<(n + 255) / 256, 256, 0, c->stream>>>(c->atlas.p, (c->atlas_w + 15) / 16, (c->atlas_h + 15) / 16, x, y, layer, w, h, tmp);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(CCU_ECUDA, "atlas write: %s", cudaGetErrorString(e));
+    return CCU_OK;
+}
+
+int ccu_scene_set_atlas(ccu_ctx *c, const uint8_t *rgba, int32_t width, int32_t height, int32_t layers) {
+    int rc = ccu_scene_atlas_create(c, width, height, layers);
+    if (rc != CCU_OK) return rc;
+    for (int l = 0; l < layers; l++) {
+        rc = ccu_scene_atlas_write(c, 0, 0, l, width, height, rgba + (size_t)l * width * height * 4);
+        if (rc != CCU_OK) return rc;
+    }
+    return CCU_OK;
+}
+
+int ccu_scene_set_sky(ccu_ctx *c, const uint8_t *rgba, int32_t res, float sky_intensity) {
+    if (!c) return fail(CCU_EINVAL, "ccu_scene_set_sky: null context");
+    if (!rgba || res <= 0 || res > 16384) return fail(CCU_EINVAL, "bad sky texture (res=%d)", res);
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    c->committed = false;
+    CU(c->sky.upload(reinterpret_cast<const uchar4 *>(rgba), (size_t)res * res, c->stream));
+    c->sky_res = res;
+    c->sky_intensity = sky_intensity;
+    return CCU_OK;
+}
+
+int ccu_scene_set_sun(ccu_ctx *c, const int32_t sun_words[6]) {
+    if (!c || !sun_words) return fail(CCU_EINVAL, "ccu_scene_set_sun: null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    c->committed = false;
+    memcpy(c->sun_host, sun_words, sizeof c->sun_host);
+    CU(c->sun_words.upload(sun_words, 6, c->stream));
+    c->have_sun = true;
+    return CCU_OK;
+}
+
+int ccu_scene_commit(ccu_ctx *c) {
+    if (!c) return fail(CCU_EINVAL, "ccu_scene_commit: null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->tree.p) return fail(CCU_ESTATE, "commit: octree not set");
+    if (!c->block_palette.p || !c->mat_palette.p) return fail(CCU_ESTATE, "commit: block/material palette not set");
+    if (!c->atlas.p) return fail(CCU_ESTATE, "commit: texture atlas not set");
+    if (!c->sky.p) return fail(CCU_ESTATE, "commit: sky not set");
+    if (!c->have_sun) return fail(CCU_ESTATE, "commit: sun not set");
+    DeviceGuard g(c->device);
+    // absent optional palettes behave as the reference's single zero word
+    int zero = 0;
+    if (!c->quad_models.p) CU(c->quad_models.upload(&zero, 0, c->stream));
+    if (!c->aabb_models.p) CU(c->aabb_models.upload(&zero, 0, c->stream));
+    if (!c->trigs.p) CU(c->trigs.upload(&zero, 0, c->stream));
+    if (!c->world_bvh.p) { CU(c->world_bvh.upload(&zero, 0, c->stream)); c->world_head.clear(); }
+    if (!c->actor_bvh.p) { CU(c->actor_bvh.upload(&zero, 0, c->stream)); c->actor_head.clear(); }
+    // sun basis on the device
+    if (!c->sun_basis.p) {
+        float z[10] = {0};
+        CU(c->sun_basis.upload(z, 10, c->stream));
+    }
+    k_sun_setup<<<1, 1, 0, c->stream>>>(c->sun_words.p, c->sun_basis.p);
+    c->launches++;
+    CU(cudaGetLastError());
+    float b[10];
+    CU(cudaMemcpyAsync(b, c->sun_basis.p, sizeof b, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    DScene &s = c->scene;
+    s.su = make_float3(b[0], b[1], b[2]);
+    s.sv = make_float3(b[3], b[4], b[5]);
+    s.sw = make_float3(b[6], b[7], b[8]);
+    s.sun_radius_cos = b[9];
+    c->committed = true;
+    return CCU_OK;
+}
+
+int ccu_camera_set(ccu_ctx *c, int32_t projector_type, const float *settings, int64_t n) {
+    if (!c || !settings) return fail(CCU_EINVAL, "ccu_camera_set: null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    if (projector_type == -1) {
+        if (n % 6 != 0 || n <= 0) return fail(CCU_EINVAL, "pre-generated rays need 6 floats per pixel (got %lld)", (long long)n);
+        cudaStreamSynchronize(c->stream);    // a render in flight may still read the old rays
+        CU(c->rays.upload(settings, (size_t)n, c->stream));
+    } else {
+        if (n < 15) return fail(CCU_EINVAL, "camera settings need 15 floats (got %lld)", (long long)n);
+        memcpy(c->cam, settings, sizeof c->cam);
+    }
+    c->projector_type = projector_type;
+    c->have_camera = true;
+    return CCU_OK;
+}
+
+int ccu_render_end(ccu_ctx *c) {
+    if (!c) return fail(CCU_EINVAL, "ccu_render_end: null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    stop_timer(c);
+    if (c->accum) cudaFree(c->accum);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    c->accum = nullptr;
+    c->pinned = nullptr;
+    c->width = c->height = 0;
+    c->window_spp = 0;
+    return CCU_OK;
+}
+
+int ccu_render_begin(ccu_ctx *c, int32_t width, int32_t height) {
+    if (!c) return fail(CCU_EINVAL, "ccu_render_begin: null context");
+    if (width <= 0 || height <= 0 || (int64_t)width * height > (1ll << 30)) return fail(CCU_EINVAL, "bad canvas %dx%d", width, height);
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    size_t n = (size_t)width * height * 3;
+    if (c->accum && (size_t)c->width * c->height * 3 != n) {
+        cudaFree(c->accum);
+        cudaFreeHost(c->pinned);
+        c->accum = nullptr;
+        c->pinned = nullptr;
+    }
+    if (!c->accum) {
+        CU(cudaMalloc(&c->accum, n * sizeof(float)));
+        CU(cudaMallocHost(&c->pinned, n * sizeof(float)));
+    }
+    CU(cudaMemsetAsync(c->accum, 0, n * sizeof(float), c->stream));
+    c->width = width;
+    c->height = height;
+    c->window_spp = 0;
+    return CCU_OK;
+}
+
+int ccu_render_set_params(ccu_ctx *c, const ccu_render_params *p) {
+    if (!c || !p) return fail(CCU_EINVAL, "ccu_render_set_params: null argument");
+    if (p->draw_depth < 0 || p->max_depth < 1) return fail(CCU_EINVAL, "bad render params");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->params = *p;
+    return CCU_OK;
+}
+
+static int render_ready(ccu_ctx *c, const char *what) {
+    if (!c->committed) return fail(CCU_ESTATE, "%s: scene not committed", what);
+    if (!c->have_camera) return fail(CCU_ESTATE, "%s: camera not set", what);
+    if (!c->accum) return fail(CCU_ESTATE, "%s: ccu_render_begin not called", what);
+    if (c->projector_type == -1 && c->rays.n != (size_t)c->width * c->height * 6)
+        return fail(CCU_ESTATE, "%s: ray buffer holds %zu floats, canvas needs %zu", what, c->rays.n, (size_t)c->width * c->height * 6);
+    return CCU_OK;
+}
+
+int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) {
+    if (!c) return fail(CCU_EINVAL, "ccu_render_passes: null context");
+    if (n_passes < 0 || (n_passes > 0 && !seeds)) return fail(CCU_EINVAL, "ccu_render_passes: bad seeds");
+    std::lock_guard<std::mutex> lk(c->mu);
+    int rc = render_ready(c, "ccu_render_passes");
+    if (rc != CCU_OK) return rc;
+    if (n_passes == 0) return CCU_OK;
+    DeviceGuard g(c->device);
+    stop_timer(c);
+    if (c->seeds_cap < n_passes) {
+        cudaStreamSynchronize(c->stream);
+        if (c->seeds_dev) cudaFree(c->seeds_dev);
+        c->seeds_dev = nullptr;
+        c->seeds_cap = 0;
+        CU(cudaMalloc(&c->seeds_dev, (size_t)std::max(n_passes, 1024) * sizeof(int)));
+        c->seeds_cap = std::max(n_passes, 1024);
+    }
+    // the seed words are the only per-pass host->device traffic (OpenClPathTracingRenderer.java:106-109)
+    CU(cudaMemcpyAsync(c->seeds_dev, seeds, (size_t)n_passes * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));   // seeds[] belongs to the caller again
+    fill_scene(c);
+    int n_pixels = c->width * c->height;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    {
+        int threads = 128;
+        int blocks = (n_pixels + threads - 1) / threads;
+        k_render_mega<<<blocks, threads, 0, c->stream>>>(c->scene, c->seeds_dev, n_passes, c->window_spp, c->accum, n_pixels);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev1, c->stream));
+    c->timing_pending = true;
+    c->window_spp += n_passes;
+    return CCU_OK;
+}
+
+int ccu_render_sync(ccu_ctx *c) {
+    if (!c) return fail(CCU_EINVAL, "ccu_render_sync: null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    stop_timer(c);
+    return CCU_OK;
+}
+
+int ccu_render_passes(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) {
+    int rc = ccu_render_passes_async(c, seeds, n_passes);
+    if (rc != CCU_OK) return rc;
+    return ccu_render_sync(c);
+}
+
+static int fetch_mean(ccu_ctx *c) {
+    size_t n = (size_t)c->width * c->height * 3;
+    CU(cudaMemcpyAsync(c->pinned, c->accum, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    stop_timer(c);
+    return CCU_OK;
+}
+
+int ccu_render_read(ccu_ctx *c, float *mean_rgb, int32_t *window_spp) {
+    if (!c || !mean_rgb) return fail(CCU_EINVAL, "ccu_render_read: null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->accum) return fail(CCU_ESTATE, "ccu_render_read: no render target");
+    DeviceGuard g(c->device);
+    int rc = fetch_mean(c);
+    if (rc != CCU_OK) return rc;
+    memcpy(mean_rgb, c->pinned, (size_t)c->width * c->height * 3 * sizeof(float));
+    if (window_spp) *window_spp = c->window_spp;
+    return CCU_OK;
+}
+
+int ccu_render_merge(ccu_ctx *c, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp) {
+    if (!c || !sample_buffer) return fail(CCU_EINVAL, "ccu_render_merge: null argument");
+    if (sample_spp < 0) return fail(CCU_EINVAL, "ccu_render_merge: negative spp");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->accum) return fail(CCU_ESTATE, "ccu_render_merge: no render target");
+    DeviceGuard g(c->device);
+    int rc = fetch_mean(c);
+    if (rc != CCU_OK) return rc;
+    int pass_spp = c->window_spp;
+    if (merged_spp) *merged_spp = pass_spp;
+    if (pass_spp == 0) return CCU_OK;
+    // OpenClPathTracingRenderer.java:167-173
+    const double sinv = 1.0 / (double)(sample_spp + pass_spp);
+    const double ds = (double)sample_spp, dp = (double)pass_spp;
+    size_t n = (size_t)c->width * c->height * 3;
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned nt = std::max(1u, std::min(16u, hw ? hw : 4u));
+    if (n < (1u << 20)) nt = 1;
+    const float *src = c->pinned;
+    auto work = [=](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) sample_buffer[i] = (sample_buffer[i] * ds + (double)src[i] * dp) * sinv;
+    };
+    if (nt == 1) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> th;
+        size_t chunk = (n + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, std::min(n, t * chunk), std::min(n, (t + 1) * chunk));
+        for (auto &t : th) t.join();
+    }
+    c->window_spp = 0;   // bufferSppReal = 0 (:170)
+    return CCU_OK;
+}
+
+int ccu_render_reset_window(ccu_ctx *c) {
+    if (!c) return fail(CCU_EINVAL, "ccu_render_reset_window: null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->window_spp = 0;
+    return CCU_OK;
+}
+
+int ccu_render_device_buffer(ccu_ctx *c, void **device_ptr, int64_t *n_floats) {
+    if (!c || !device_ptr) return fail(CCU_EINVAL, "ccu_render_device_buffer: null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->accum) return fail(CCU_ESTATE, "ccu_render_device_buffer: no render target");
+    *device_ptr = c->accum;
+    if (n_floats) *n_floats = (int64_t)c->width * c->height * 3;
+    return CCU_OK;
+}
+
+int ccu_render_scale(ccu_ctx *c, float factor) {
+    if (!c) return fail(CCU_EINVAL, "ccu_render_scale: null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->accum) return fail(CCU_ESTATE, "ccu_render_scale: no render target");
+    DeviceGuard g(c->device);
+    size_t n = (size_t)c->width * c->height * 3;
+    k_scale<<<c->sm_count * 4, 256, 0, c->stream>>>(c->accum, factor, n);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return CCU_OK;
+}
+
+int ccu_stream_handle(ccu_ctx *c, void **cuda_stream) {
+    if (!c || !cuda_stream) return fail(CCU_EINVAL, "ccu_stream_handle: null argument");
+    *cuda_stream = (void *)c->stream;
+    return CCU_OK;
+}
+
+int ccu_first_hit(ccu_ctx *c, int32_t seed, int32_t *block, int32_t *face, int32_t *node, int32_t *kind, float *t, float *normal,
+                  float *color) {
+    if (!c) return fail(CCU_EINVAL, "ccu_first_hit: null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    int rc = render_ready(c, "ccu_first_hit");
+    if (rc != CCU_OK) return rc;
+    DeviceGuard g(c->device);
+    stop_timer(c);
+    size_t n = (size_t)c->width * c->height;
+    // one scratch allocation: 4 int planes, t, normal(3), color(4) = 12 words per pixel
+    int *scratch = nullptr;
+    CU(cudaMalloc(&scratch, n * 12 * sizeof(int)));
+    int *d_block = scratch, *d_face = scratch + n, *d_node = scratch + 2 * n, *d_kind = scratch + 3 * n;
+    float *d_color = reinterpret_cast<float *>(scratch + 4 * n);          // 16-byte aligned: n*16 bytes offset
+    float *d_t = reinterpret_cast<float *>(scratch + 8 * n);
+    float *d_normal = reinterpret_cast<float *>(scratch + 9 * n);
+    fill_scene(c);
+    cudaEventRecord(c->ev0, c->stream);
+    k_first_hit<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color);
+    c->launches++;
+    cudaEventRecord(c->ev1, c->stream);
+    c->timing_pending = true;
+    cudaError_t e = cudaGetLastError();
+    auto back = [&](void *dst, const void *src, size_t bytes) {
+        if (dst && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+    };
+    back(block, d_block, n * 4); back(face, d_face, n * 4); back(node, d_node, n * 4); back(kind, d_kind, n * 4);
+    back(t, d_t, n * 4); back(normal, d_normal, n * 12); back(color, d_color, n * 16);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(scratch);
+    if (e != cudaSuccess) return fail(CCU_ECUDA, "ccu_first_hit: %s", cudaGetErrorString(e));
+    stop_timer(c);
+    return CCU_OK;
+}
+
+int ccu_preview(ccu_ctx *c, int32_t *argb) {
+    if (!c || !argb) return fail(CCU_EINVAL, "ccu_preview: null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    int rc = render_ready(c, "ccu_preview");
+    if (rc != CCU_OK) return rc;
+    DeviceGuard g(c->device);
+    stop_timer(c);
+    size_t n = (size_t)c->width * c->height;
+    int *d = nullptr;
+    CU(cudaMalloc(&d, n * sizeof(int)));
+    fill_scene(c);
+    cudaEventRecord(c->ev0, c->stream);
+    k_preview<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, (int)n, d);
+    c->launches++;
+    cudaEventRecord(c->ev1, c->stream);
+    c->timing_pending = true;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(argb, d, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(CCU_ECUDA, "ccu_preview: %s", cudaGetErrorString(e));
+    stop_timer(c);
+    return CCU_OK;
+}
+
+int ccu_last_kernel_ms(ccu_ctx *c, float *ms) {
+    if (!c || !ms) return fail(CCU_EINVAL, "ccu_last_kernel_ms: null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    stop_timer(c);
+    *ms = c->last_ms;
+    return CCU_OK;
+}
+
+int ccu_launch_count(ccu_ctx *c, int64_t *launches) {
+    if (!c || !launches) return fail(CCU_EINVAL, "ccu_launch_count: null argument");
+    *launches = c->launches;
+    return CCU_OK;
+}
+
+int ccu_scene_device_bytes(ccu_ctx *c, int64_t *bytes) {
+    if (!c || !bytes) return fail(CCU_EINVAL, "ccu_scene_device_bytes: null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    *bytes = (int64_t)(c->tree.bytes() + c->block_palette.bytes() + c->quad_models.bytes() + c->aabb_models.bytes() + c->mat_palette.bytes() +
+                       c->trigs.bytes() + c->world_bvh.bytes() + c->actor_bvh.bytes() + c->atlas.bytes() + c->sky.bytes());
+    return CCU_OK;
+}
+
+}  // extern "C"

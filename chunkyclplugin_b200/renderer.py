@@ -1,0 +1,283 @@
+"""Host-side mirror of the reference's renderer classes, driving the C ABI instead of JOCL.
+
+The reference's host is Java inside Chunky (no JVM or chunky-core in this image), so this module is the
+host that stands in for it: same class roles, method names, call order and error behaviour as
+
+  reference (dev.thatredox.chunkynative.opencl)        here
+  -------------------------------------------------    -------------------------------------------
+  renderer/RendererInstance.java                       RendererInstance
+  renderer/ClSceneLoader.java (+ AbstractSceneLoader)  CudaSceneLoader   (alias ClSceneLoader)
+  renderer/scene/ClCamera.java                         CudaCamera        (alias ClCamera)
+  OpenClPathTracingRenderer.java                       CudaPathTracingRenderer (alias OpenClPathTracingRenderer)
+  OpenClPreviewRenderer.java                           CudaPreviewRenderer     (alias OpenClPreviewRenderer)
+
+``Scene`` / ``DefaultRenderManager`` are minimal stand-ins for the Chunky objects those classes touch
+(sample buffer, spp counters, snapshot control, redraw).  The Java shim in java/ makes the same calls.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import native
+from .javarandom import JavaRandom
+from .scenes import PackedScene
+
+
+# ----------------------------------------------------------------------------------------------------
+# Chunky stand-ins
+# ----------------------------------------------------------------------------------------------------
+class Scene:
+    """What the renderers use of se.llbit.chunky.renderer.scene.Scene."""
+
+    def __init__(self, packed: PackedScene, target_spp: int = 16):
+        self.packed = packed
+        self.width, self.height = packed.width, packed.height
+        self.sample_buffer = np.zeros(self.width * self.height * 3, dtype=np.float64)   # getSampleBuffer()
+        self.back_buffer = np.zeros(self.width * self.height, dtype=np.int32)           # getBackBuffer().data
+        self.spp = 0
+        self.target_spp = target_spp
+        self.finalize_buffer = False
+        self.post_process_calls = 0
+
+    def getSampleBuffer(self): return self.sample_buffer
+    def getTargetSpp(self): return self.target_spp
+    def shouldFinalizeBuffer(self): return self.finalize_buffer
+    def postProcessFrame(self): self.post_process_calls += 1
+
+
+class SnapshotControl:
+    """Save events: at the target spp and optionally every ``dump_frequency`` spp."""
+
+    def __init__(self, dump_frequency: int = 0):
+        self.dump_frequency = dump_frequency
+
+    def saveSnapshot(self, scene: Scene, spp: int) -> bool:
+        return spp >= scene.target_spp
+
+    def saveRenderDump(self, scene: Scene, spp: int) -> bool:
+        return self.dump_frequency > 0 and spp % self.dump_frequency == 0
+
+
+class DefaultRenderManager:
+    def __init__(self, scene: Scene, snapshot_control: Optional[SnapshotControl] = None):
+        self.bufferedScene = scene
+        self.snapshot_control = snapshot_control or SnapshotControl()
+        self.redraws = 0
+
+    def getSnapshotControl(self): return self.snapshot_control
+    def redrawScreen(self): self.redraws += 1
+    def shouldFinalize(self): return False
+
+
+# ----------------------------------------------------------------------------------------------------
+# RendererInstance.java:23-28,31-110 - device selection + context singleton
+# ----------------------------------------------------------------------------------------------------
+class RendererInstance:
+    _instance: Optional["RendererInstance"] = None
+    _lock = threading.Lock()
+    persistent_settings = {"clDevice": 0}          # PersistentSettings int "clDevice" (RendererInstance.java:33)
+
+    def __init__(self, device_index: Optional[int] = None):
+        n = native.device_count()                   # raises (no fallback) when no CUDA device exists
+        self.devices = [native.device_info(i) for i in range(n)]
+        idx = self.persistent_settings.get("clDevice", 0) if device_index is None else device_index
+        if not 0 <= idx < n:
+            idx = 0                                 # RendererInstance.java:74: falls back to the first device
+        self.device_index = idx
+        self.context = native.Context(idx)
+
+    @classmethod
+    def get(cls, device_index: Optional[int] = None) -> "RendererInstance":
+        with cls._lock:
+            if cls._instance is None or (device_index is not None and cls._instance.device_index != device_index):
+                if cls._instance is not None:
+                    cls._instance.context.close()
+                cls._instance = RendererInstance(device_index)
+            return cls._instance
+
+    @classmethod
+    def reset(cls):
+        with cls._lock:
+            if cls._instance is not None:
+                cls._instance.context.close()
+            cls._instance = None
+
+
+# ----------------------------------------------------------------------------------------------------
+# ClSceneLoader.java + AbstractSceneLoader.java:42-162
+# ----------------------------------------------------------------------------------------------------
+class CudaSceneLoader:
+    def __init__(self, instance: Optional[RendererInstance] = None):
+        self.instance = instance or RendererInstance.get()
+        self.modCount = 0
+        self._loaded_scene_id = None
+
+    def ensureLoad(self, scene: Scene) -> bool:                        # AbstractSceneLoader.java:42-55
+        if self._loaded_scene_id != id(scene.packed):
+            self.modCount = -1
+            return self.load(0, "SCENE_LOADED", scene)
+        return True
+
+    def load(self, modCount: int, resetReason: str, scene: Scene) -> bool:    # :60-162
+        if self.modCount == modCount:
+            return True
+        if resetReason in ("NONE", "MODE_CHANGE"):
+            self.modCount = modCount
+            return True
+        p, ctx = scene.packed, self.instance.context
+        ctx.scene_begin()
+        ctx.set_atlas(p.atlas)                      # ClTextureLoader.buildTextures
+        ctx.set_block_palette(p.block_palette)
+        ctx.set_material_palette(p.mat_palette)
+        ctx.set_aabb_models(p.aabb_models)
+        ctx.set_quad_models(p.quad_models)
+        ctx.set_triangles(p.bvh_trigs)
+        ctx.set_world_bvh(p.world_bvh)
+        ctx.set_actor_bvh(p.actor_bvh)
+        ctx.set_sun(p.sun)
+        ctx.set_sky(p.sky, p.sky_intensity)         # ClSky
+        ctx.set_octree(p.octree, p.octree_depth)    # loadOctree, ClSceneLoader.java:52-63
+        ctx.scene_commit()
+        self.modCount = modCount
+        self._loaded_scene_id = id(p)
+        return True
+
+
+# ----------------------------------------------------------------------------------------------------
+# ClCamera.java:33-105
+# ----------------------------------------------------------------------------------------------------
+class CudaCamera:
+    def __init__(self, scene: Scene, instance: Optional[RendererInstance] = None):
+        self.instance = instance or RendererInstance.get()
+        self.scene = scene
+        self.projectorType = scene.packed.projector_type
+        self.needGenerate = self.projectorType == -1
+        if not self.needGenerate:
+            self.instance.context.camera_set(self.projectorType, scene.packed.camera[:15])
+
+    def generate(self, renderLock=None, jitter: bool = True):
+        if not self.needGenerate:
+            return
+        rays = self.scene.packed.camera        # pre-generated by the host (Chunky's Camera.calcViewRay in the reference)
+        if renderLock is not None:
+            renderLock.acquire()
+        try:
+            self.instance.context.camera_set(-1, rays)
+        finally:
+            if renderLock is not None:
+                renderLock.release()
+
+    def close(self): pass
+
+
+# ----------------------------------------------------------------------------------------------------
+# OpenClPathTracingRenderer.java
+# ----------------------------------------------------------------------------------------------------
+class CudaPathTracingRenderer:
+    MERGE_WINDOW = 1024                                       # :158
+
+    def __init__(self, sceneLoader: Optional[CudaSceneLoader] = None, passes_per_call: int = 0):
+        self.sceneLoader = sceneLoader or CudaSceneLoader()
+        self.postRender: Callable[[], bool] = lambda: False   # Chunky passes a callback that returns true to stop
+        # how many passes one C-ABI call may cover (0 = up to the next merge point); the reference issues 1 per launch
+        self.passes_per_call = passes_per_call
+        self.kernel_ms = 0.0
+
+    def getId(self): return "ChunkyClRenderer"               # :33-36 - the renderer selector id is unchanged
+    def getName(self): return "ChunkyClRenderer"
+    def getDescription(self): return "ChunkyClRenderer"
+    def setPostRender(self, callback): self.postRender = callback
+    def autoPostProcess(self): return False                  # :197-200
+
+    def sceneReset(self, manager: DefaultRenderManager, reason: str, resetCount: int):     # :203-205
+        self.sceneLoader.load(resetCount, reason, manager.bufferedScene)
+
+    def render(self, manager: DefaultRenderManager):         # :54-191
+        instance = self.sceneLoader.instance
+        ctx = instance.context
+        renderLock = threading.Lock()
+        scene = manager.bufferedScene
+        sampleBuffer = scene.getSampleBuffer()
+
+        self.sceneLoader.ensureLoad(scene)                   # :64
+        camera = CudaCamera(scene, instance)                 # :70
+        ctx.render_begin(scene.width, scene.height)          # :71-78
+        try:
+            camera.generate(renderLock, True)                # :88
+            bufferSppReal = 0
+            logicalSpp = scene.spp
+            sceneSpp = scene.spp
+            rand = JavaRandom(0)                             # :95
+            self.kernel_ms = 0.0
+            while logicalSpp < scene.getTargetSpp():         # :102
+                remaining_to_target = scene.getTargetSpp() - (logicalSpp + bufferSppReal)
+                n = min(self.MERGE_WINDOW - bufferSppReal, max(remaining_to_target, 1))
+                if self.passes_per_call > 0:
+                    n = min(n, self.passes_per_call)
+                seeds = np.array([rand.next_int() for _ in range(n)], dtype=np.int32)      # :106-107
+                with renderLock:
+                    ctx.render_passes(seeds)                 # :108-141 (bufferSpp tracked by the library)
+                self.kernel_ms += ctx.last_kernel_ms()
+                bufferSppReal += n                           # :143-144
+                scene.spp += n
+                saveEvent = self._isSaveEvent(manager.getSnapshotControl(), scene, logicalSpp + bufferSppReal)
+                if not scene.shouldFinalizeBuffer() and not saveEvent:
+                    if self.postRender():                    # :153-157
+                        break
+                    if bufferSppReal < self.MERGE_WINDOW:    # :158-159
+                        continue
+                if self.postRender():                        # :163
+                    break
+                passSpp = ctx.render_merge(sampleBuffer, sceneSpp)     # :164-173 (read + weighted merge, window reset)
+                assert passSpp == bufferSppReal
+                sceneSpp += passSpp
+                bufferSppReal = 0
+                scene.postProcessFrame()                     # :175-176
+                manager.redrawScreen()
+                logicalSpp += passSpp                        # :178
+        finally:
+            camera.close()
+            ctx.render_end()
+
+    @staticmethod
+    def _isSaveEvent(control: SnapshotControl, scene: Scene, spp: int) -> bool:           # :193-195
+        return control.saveSnapshot(scene, spp) or control.saveRenderDump(scene, spp)
+
+
+# ----------------------------------------------------------------------------------------------------
+# OpenClPreviewRenderer.java:47-115
+# ----------------------------------------------------------------------------------------------------
+class CudaPreviewRenderer:
+    def __init__(self, sceneLoader: Optional[CudaSceneLoader] = None):
+        self.sceneLoader = sceneLoader or CudaSceneLoader()
+
+    def getId(self): return "ChunkyClPreviewRenderer"
+    def getName(self): return "ChunkyClPreviewRenderer"
+    def getDescription(self): return "ChunkyClPreviewRenderer"
+    def autoPostProcess(self): return False
+
+    def sceneReset(self, manager, reason, resetCount):
+        self.sceneLoader.load(resetCount, reason, manager.bufferedScene)
+
+    def render(self, manager: DefaultRenderManager):
+        scene = manager.bufferedScene
+        ctx = self.sceneLoader.instance.context
+        self.sceneLoader.ensureLoad(scene)
+        camera = CudaCamera(scene, self.sceneLoader.instance)
+        ctx.render_begin(scene.width, scene.height)
+        try:
+            camera.generate(None, False)
+            scene.back_buffer[:] = ctx.preview()
+            manager.redrawScreen()
+        finally:
+            ctx.render_end()
+
+
+# reference-named aliases, so code written against the reference's class names reads the same
+ClSceneLoader = CudaSceneLoader
+ClCamera = CudaCamera
+OpenClPathTracingRenderer = CudaPathTracingRenderer
+OpenClPreviewRenderer = CudaPreviewRenderer

@@ -1,0 +1,127 @@
+/*
+ * chunkycu.h - C ABI of libchunkycu.so, the B200-native (sm_100a CUDA) replacement for the OpenCL
+ * device layer of the ChunkyCL plugin.
+ *
+ * This is the drop-in boundary: every entry point replaces a group of JOCL calls in the reference
+ * (file:line citations are into /root/reference/src/main/java/dev/thatredox/chunkynative/).  A Java
+ * host binds them through JNI or the FFM API (INTEGRATION.md shows the stubs); the Python host in
+ * chunkyclplugin_b200/ binds the same symbols through ctypes.
+ *
+ * Conventions
+ *   - plain C types only; host pointers are read/written during the call and never retained
+ *     (the reference passes Pointer.to(javaArray) with blocking transfers, e.g. ClIntBuffer.java:22-24);
+ *   - every function returns CCU_OK (0) or a negative CCU_E* code; ccu_last_error() returns the
+ *     message of the calling thread's last failure (the reference runs with
+ *     CL.setExceptionsEnabled(true), RendererInstance.java:36 - the Java shim turns non-zero into
+ *     RuntimeException);
+ *   - a ccu_ctx is bound to one CUDA device and is internally locked: entry points may be called from
+ *     any thread (render thread, ForkJoin merge tasks, the cleaner thread - SURVEY.md 8b "threading");
+ *   - there is no CPU fallback: without a CUDA device every call fails with CCU_ENODEVICE.
+ */
+#ifndef CHUNKYCU_H
+#define CHUNKYCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCU_OK 0
+#define CCU_ENODEVICE (-1) /* no CUDA device / driver (UnsatisfiedLinkError path, opencl/ChunkyCl.java:37-40) */
+#define CCU_EINVAL (-2)    /* bad argument or call order */
+#define CCU_ECUDA (-3)     /* a CUDA runtime call failed */
+#define CCU_ENOMEM (-4)
+#define CCU_ESTATE (-5)    /* scene/camera/render target not ready */
+
+typedef struct ccu_ctx ccu_ctx;
+
+/* launch parameters; the reference hard-codes 256 / 5 / 13.0f (rayTracer.cl:94,99,103,107) */
+typedef struct ccu_render_params {
+    int32_t draw_depth;    /* octree march step limit */
+    int32_t max_depth;     /* ray depth limit (5 = 4 bounces) */
+    float emitter_scale;   /* emitter intensity factor */
+    int32_t kernel;        /* 0 = auto, 1 = megakernel (thread per pixel), 2 = persistent wavefront */
+} ccu_render_params;
+
+/* ---- device enumeration: RendererInstance.java:39-75,123-157 (clGetPlatformIDs/clGetDeviceIDs/clGetDeviceInfo),
+ *      used by the GPU selector UI (ui/GpuSelector.java:24-87) -------------------------------------------------- */
+int ccu_device_count(int *count);
+int ccu_device_info(int index, char *name, int name_len, int *sm_count, int *clock_khz, uint64_t *mem_bytes);
+
+/* ---- context: RendererInstance.java:81-101 (clCreateContext + clCreateCommandQueue); no runtime compile step
+ *      (KernelLoader.java:17-60 has no equivalent: kernels are built ahead of time for sm_100a) ----------------- */
+int ccu_ctx_create(int device_index, ccu_ctx **out);
+int ccu_ctx_destroy(ccu_ctx *ctx); /* idempotent on NULL; ClMemory.java:12-16 / NativeCleaner.java:38-53 */
+const char *ccu_last_error(void);
+const char *ccu_version(void);
+
+/* ---- scene upload: ClSceneLoader.java:39-63, ClIntBuffer.java:14-25, ClPackedResourcePalette.java:14-26,
+ *      AbstractSceneLoader.java:60-162.  Arrays use the reference's packed int layouts unchanged; zero-length
+ *      arrays are accepted (the reference uploads a single 0 int, ClIntBuffer.java:15-18). ---------------------- */
+int ccu_scene_begin(ccu_ctx *ctx);
+int ccu_scene_set_octree(ccu_ctx *ctx, const int32_t *tree_data, int64_t n, int32_t depth); /* ClSceneLoader.java:52-63 (leaves already remapped, :56-58) */
+int ccu_scene_set_block_palette(ccu_ctx *ctx, const int32_t *words, int64_t n);    /* ClSceneLoader.getBlockPalette :110 */
+int ccu_scene_set_quad_models(ccu_ctx *ctx, const int32_t *words, int64_t n);      /* getQuadPalette :125 */
+int ccu_scene_set_aabb_models(ccu_ctx *ctx, const int32_t *words, int64_t n);      /* getAabbPalette :120 */
+int ccu_scene_set_material_palette(ccu_ctx *ctx, const int32_t *words, int64_t n); /* getMaterialPalette :115 */
+int ccu_scene_set_triangles(ccu_ctx *ctx, const int32_t *words, int64_t n);        /* getTrigPalette :130 */
+int ccu_scene_set_world_bvh(ccu_ctx *ctx, const int32_t *words, int64_t n);        /* getWorldBvh :135 */
+int ccu_scene_set_actor_bvh(ccu_ctx *ctx, const int32_t *words, int64_t n);        /* getActorBvh :139 */
+/* texture atlas: ClTextureLoader.java:46-66 - clCreateImage(8192x8192xlayers RGBA8) then one clEnqueueWriteImage
+ * per texture at (16*tileX, 16*tileY, layer) */
+int ccu_scene_atlas_create(ccu_ctx *ctx, int32_t width, int32_t height, int32_t layers);
+int ccu_scene_atlas_write(ccu_ctx *ctx, int32_t x, int32_t y, int32_t layer, int32_t w, int32_t h, const uint8_t *rgba);
+/* whole-image convenience (row-major [layers][height][width][4]) */
+int ccu_scene_set_atlas(ccu_ctx *ctx, const uint8_t *rgba, int32_t width, int32_t height, int32_t layers);
+int ccu_scene_set_sky(ccu_ctx *ctx, const uint8_t *rgba, int32_t resolution, float sky_intensity); /* ClSky.java:23-62 */
+int ccu_scene_set_sun(ccu_ctx *ctx, const int32_t sun_words[6]);                                   /* ClSceneLoader.getSun :148, PackedSun.java:31-41 */
+int ccu_scene_commit(ccu_ctx *ctx); /* builds the traversal layout in HBM; scene is immutable until the next begin */
+
+/* ---- camera: ClCamera.java:33-70 (settings buffer) and :72-105 (pre-generated ray upload) -------------------- */
+int ccu_camera_set(ccu_ctx *ctx, int32_t projector_type, const float *settings, int64_t n_floats);
+
+/* ---- path tracing: OpenClPathTracingRenderer.java:54-191 ------------------------------------------------------ */
+int ccu_render_begin(ccu_ctx *ctx, int32_t width, int32_t height);   /* :71-78 accumulation buffer (zeros), width/height buffers */
+int ccu_render_set_params(ccu_ctx *ctx, const ccu_render_params *p); /* optional; defaults = reference constants */
+/* :102-144 for n_passes consecutive passes: pass i uses seeds[i] (the host draws rand.nextInt() per pass, :106-107)
+ * and bufferSpp = passes already in the window (:108-109); blocks until the device is done (:141). */
+int ccu_render_passes(ccu_ctx *ctx, const int32_t *seeds, int32_t n_passes);
+int ccu_render_passes_async(ccu_ctx *ctx, const int32_t *seeds, int32_t n_passes); /* same, returns after enqueue */
+int ccu_render_sync(ccu_ctx *ctx);
+/* :164-166 blocking read of the running-mean buffer float[3*W*H]; *window_spp = passes accumulated in the window */
+int ccu_render_read(ccu_ctx *ctx, float *mean_rgb, int32_t *window_spp);
+/* :167-173 fused read + merge into Chunky's double sample buffer:
+ *   sample[i] = (sample[i]*sample_spp + mean[i]*window_spp) / (sample_spp + window_spp); then the window restarts (:170) */
+int ccu_render_merge(ccu_ctx *ctx, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp);
+int ccu_render_reset_window(ccu_ctx *ctx); /* bufferSppReal = 0 (:170); the buffer itself is not cleared, as in the reference */
+int ccu_render_end(ccu_ctx *ctx);          /* releases the per-render buffers (:80-85 try-with-resources) */
+
+/* multi-GPU plumbing: device pointer of the running-mean buffer (float[3*W*H]) so that the host's
+ * communication layer (NCCL) can reduce per-GPU buffers without a host round trip, and a scaling hook
+ * that turns the mean into a window sum (mean * window_spp) before the reduce. */
+int ccu_render_device_buffer(ccu_ctx *ctx, void **device_ptr, int64_t *n_floats);
+int ccu_render_scale(ccu_ctx *ctx, float factor);
+int ccu_stream_handle(ccu_ctx *ctx, void **cuda_stream);
+
+/* ---- first-hit buffers for the camera rays (BASELINE config 2); built on closestIntersect kernel.h:14-24 ------
+ * block  = record.material (block palette pointer, 0 on miss)   face = 0..5 (-x,+x,-y,+y,-z,+z) or 6
+ * node   = index of the hit leaf in the uploaded treeData (-1 on miss / BVH hit)
+ * kind   = 0 miss, 1 octree, 2 world BVH, 3 actor BVH            t = record.distance (+inf on miss)
+ * normal = float[3*W*H], color = float[4*W*H]; any output pointer may be NULL. */
+int ccu_first_hit(ccu_ctx *ctx, int32_t seed, int32_t *block, int32_t *face, int32_t *node, int32_t *kind, float *t,
+                  float *normal, float *color);
+
+/* ---- preview: OpenClPreviewRenderer.java:47-115 (kernel rayTracer.cl:115-217), ARGB int[W*H] ----------------- */
+int ccu_preview(ccu_ctx *ctx, int32_t *argb);
+
+/* ---- instrumentation ------------------------------------------------------------------------------------------ */
+int ccu_last_kernel_ms(ccu_ctx *ctx, float *ms);          /* CUDA-event time of the last render_passes / first_hit launch(es) */
+int ccu_launch_count(ccu_ctx *ctx, int64_t *launches);    /* kernels launched by this context so far */
+int ccu_scene_device_bytes(ccu_ctx *ctx, int64_t *bytes); /* HBM held by the committed scene */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHUNKYCU_H */
