@@ -1,7 +1,7 @@
 // ccu_math.cuh - fp32 vector helpers and the deterministic transcendental set ("detmath").
 //
-// Arithmetic contract: every fp32 operation is one IEEE-754 round-to-nearest operation in the
-// order written.  The translation unit is compiled with -fmad=false (no contraction), default
+// Arithmetic contract: every fp32 operation the reference writes out is one IEEE-754
+// round-to-nearest operation in the order written; the OpenCL vector builtins expand as NVIDIA's runtime does.  The translation unit is compiled with -fmad=false (no contraction), default
 // -prec-div=true -prec-sqrt=true -ftz=false.  sin/cos/atan2/asin/acos are fixed polynomial kernels built
 // from +,-,*,/,sqrt,floor only, so the full path - not just the integer first-hit buffers - reproduces
 // bit-for-bit on any IEEE machine.  (The reference calls the OpenCL builtins cos/sin/atan2/asin/acos,
@@ -24,13 +24,25 @@ __device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x 
 __device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
 __device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ float dot3(float3 a, float3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+// dot / cross / normalize stand for the OpenCL builtins of the same name and are expanded exactly as the
+// NVIDIA OpenCL runtime expands them (explicit fused multiply-adds; PTX evidence: profiles/clref_vec_strict.ptx).
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, a.y * b.y)); }
 __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
-    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    return f3(__fmaf_rn(a.y, b.z, -(a.z * b.y)), __fmaf_rn(a.z, b.x, -(a.x * b.z)), __fmaf_rn(a.x, b.y, -(a.y * b.x)));
 }
-__device__ __forceinline__ float3 normalize3(float3 a) {
-    float inv = 1.0f / sqrtf(dot3(a, a));
-    return a * inv;
+__device__ __forceinline__ float3 normalize3(float3 v) {
+    const float inf = __int_as_float(0x7f800000), qnan = __int_as_float(0x7fc00000);
+    float ax = fabsf(v.x), ay = fabsf(v.y), az = fabsf(v.z);
+    if (ax != ax || ay != ay || az != az) return f3(qnan, qnan, qnan);
+    float m = (ax < ay) ? ay : ax;
+    m = (m < az) ? az : m;
+    if (m == 0.0f) return f3(0, 0, 0);
+    if (m == inf) return f3(v.x / inf, v.y / inf, v.z / inf);
+    float a = ax / m, b = ay / m, c = az / m;
+    float r = sqrtf(__fmaf_rn(c, c, __fmaf_rn(a, a, b * b)));
+    float len = m * r;
+    if (fabsf(len) != inf) return f3(v.x / len, v.y / len, v.z / len);
+    return f3((v.x / r) / m, (v.y / r) / m, (v.z / r) / m);
 }
 // cvt.rzi.s32.f32: toward zero, saturating, NaN -> 0
 __device__ __forceinline__ int f2i(float f) { return __float2int_rz(f); }

@@ -219,6 +219,7 @@ struct ccu_ctx {
     int *seeds_dev = nullptr;
     int seeds_cap = 0;
     int window_spp = 0;
+    bool target_live = false;    // between ccu_render_begin and ccu_render_end
     ccu_render_params params = {256, 5, 13.0f, 0};
 
     float last_ms = 0;
@@ -547,11 +548,8 @@ int ccu_render_end(ccu_ctx *c) {
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
     stop_timer(c);
-    if (c->accum) cudaFree(c->accum);
-    if (c->pinned) cudaFreeHost(c->pinned);
-    c->accum = nullptr;
-    c->pinned = nullptr;
-    c->width = c->height = 0;
+    // the buffers stay cached for the next render of the same size (freed by ccu_ctx_destroy / a size change)
+    c->target_live = false;
     c->window_spp = 0;
     return CCU_OK;
 }
@@ -577,6 +575,7 @@ int ccu_render_begin(ccu_ctx *c, int32_t width, int32_t height) {
     c->width = width;
     c->height = height;
     c->window_spp = 0;
+    c->target_live = true;
     return CCU_OK;
 }
 
@@ -591,7 +590,7 @@ int ccu_render_set_params(ccu_ctx *c, const ccu_render_params *p) {
 static int render_ready(ccu_ctx *c, const char *what) {
     if (!c->committed) return fail(CCU_ESTATE, "%s: scene not committed", what);
     if (!c->have_camera) return fail(CCU_ESTATE, "%s: camera not set", what);
-    if (!c->accum) return fail(CCU_ESTATE, "%s: ccu_render_begin not called", what);
+    if (!c->accum || !c->target_live) return fail(CCU_ESTATE, "%s: ccu_render_begin not called", what);
     if (c->projector_type == -1 && c->rays.n != (size_t)c->width * c->height * 6)
         return fail(CCU_ESTATE, "%s: ray buffer holds %zu floats, canvas needs %zu", what, c->rays.n, (size_t)c->width * c->height * 6);
     return CCU_OK;
@@ -659,7 +658,7 @@ static int fetch_mean(ccu_ctx *c) {
 int ccu_render_read(ccu_ctx *c, float *mean_rgb, int32_t *window_spp) {
     if (!c || !mean_rgb) return fail(CCU_EINVAL, "ccu_render_read: null argument");
     std::lock_guard<std::mutex> lk(c->mu);
-    if (!c->accum) return fail(CCU_ESTATE, "ccu_render_read: no render target");
+    if (!c->accum || !c->target_live) return fail(CCU_ESTATE, "ccu_render_read: no render target");
     DeviceGuard g(c->device);
     int rc = fetch_mean(c);
     if (rc != CCU_OK) return rc;
@@ -672,7 +671,7 @@ int ccu_render_merge(ccu_ctx *c, double *sample_buffer, int32_t sample_spp, int3
     if (!c || !sample_buffer) return fail(CCU_EINVAL, "ccu_render_merge: null argument");
     if (sample_spp < 0) return fail(CCU_EINVAL, "ccu_render_merge: negative spp");
     std::lock_guard<std::mutex> lk(c->mu);
-    if (!c->accum) return fail(CCU_ESTATE, "ccu_render_merge: no render target");
+    if (!c->accum || !c->target_live) return fail(CCU_ESTATE, "ccu_render_merge: no render target");
     DeviceGuard g(c->device);
     int rc = fetch_mean(c);
     if (rc != CCU_OK) return rc;
@@ -712,7 +711,7 @@ int ccu_render_reset_window(ccu_ctx *c) {
 int ccu_render_device_buffer(ccu_ctx *c, void **device_ptr, int64_t *n_floats) {
     if (!c || !device_ptr) return fail(CCU_EINVAL, "ccu_render_device_buffer: null argument");
     std::lock_guard<std::mutex> lk(c->mu);
-    if (!c->accum) return fail(CCU_ESTATE, "ccu_render_device_buffer: no render target");
+    if (!c->accum || !c->target_live) return fail(CCU_ESTATE, "ccu_render_device_buffer: no render target");
     *device_ptr = c->accum;
     if (n_floats) *n_floats = (int64_t)c->width * c->height * 3;
     return CCU_OK;
@@ -721,7 +720,7 @@ int ccu_render_device_buffer(ccu_ctx *c, void **device_ptr, int64_t *n_floats) {
 int ccu_render_scale(ccu_ctx *c, float factor) {
     if (!c) return fail(CCU_EINVAL, "ccu_render_scale: null context");
     std::lock_guard<std::mutex> lk(c->mu);
-    if (!c->accum) return fail(CCU_ESTATE, "ccu_render_scale: no render target");
+    if (!c->accum || !c->target_live) return fail(CCU_ESTATE, "ccu_render_scale: no render target");
     DeviceGuard g(c->device);
     size_t n = (size_t)c->width * c->height * 3;
     k_scale<<<c->sm_count * 4, 256, 0, c->stream>>>(c->accum, factor, n);

@@ -18,8 +18,12 @@
  * Image sampling follows OpenCL 1.2 section 8.2.
  *
  * Arithmetic contract (shared with the CUDA build, see DESIGN.md "Arithmetic contract"):
- *   - every fp32 operation is a single IEEE-754 round-to-nearest operation, in source order,
- *     no contraction (build with -ffp-contract=off; the CUDA side uses -fmad=false);
+ *   - every fp32 operation the reference writes out is a single IEEE-754 round-to-nearest operation, in
+ *     source order, no contraction (build with -ffp-contract=off; the CUDA side uses -fmad=false) - i.e.
+ *     the reference kernel under "#pragma OPENCL FP_CONTRACT OFF" + -cl-fp32-correctly-rounded-divide-sqrt;
+ *   - the vector builtins dot/cross/normalize expand as the NVIDIA OpenCL runtime expands them (explicit
+ *     fmaf, see vdot/vcross/vnormalize), so that this file reproduces that build of the reference bit for
+ *     bit wherever no transcendental function is involved;
  *   - the reference's implicit double promotions (unsuffixed literals) are kept as doubles;
  *   - float->int conversion saturates and maps NaN to 0 (what cvt.rzi.s32.f32 does on the GPU the
  *     reference runs on; plain C would be UB);
@@ -96,9 +100,26 @@ static inline v3 vadd(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
 static inline v3 vsub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
 static inline v3 vmul(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
 static inline v3 vscale(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
-static inline float vdot(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
-static inline v3 vcross(v3 a, v3 b) { return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-static inline v3 vnormalize(v3 a) { float inv = 1.0f / sqrtf(vdot(a, a)); return vscale(a, inv); }
+/* The OpenCL vector builtins dot / cross / normalize, expanded exactly as the NVIDIA OpenCL runtime expands
+ * them (PTX of oracle/clref probe_vec, kept in profiles/clref_vec_strict.ptx): these are library code and use
+ * fused multiply-adds even under "#pragma OPENCL FP_CONTRACT OFF". */
+static inline float vdot(v3 a, v3 b) { return fmaf(a.z, b.z, fmaf(a.x, b.x, a.y * b.y)); }
+static inline v3 vcross(v3 a, v3 b) {
+    return V(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+static inline v3 vnormalize(v3 v) {
+    float ax = fabsf(v.x), ay = fabsf(v.y), az = fabsf(v.z);
+    if (ax != ax || ay != ay || az != az) return V(NAN, NAN, NAN);
+    float m = (ax < ay) ? ay : ax;
+    m = (m < az) ? az : m;
+    if (m == 0.0f) return V(0, 0, 0);
+    if (m == HUGE_VALF) return V(v.x / HUGE_VALF, v.y / HUGE_VALF, v.z / HUGE_VALF);
+    float a = ax / m, b = ay / m, c = az / m;
+    float r = sqrtf(fmaf(c, c, fmaf(a, a, b * b)));
+    float len = m * r;
+    if (fabsf(len) != HUGE_VALF) return V(v.x / len, v.y / len, v.z / len);
+    return V((v.x / r) / m, (v.y / r) / m, (v.z / r) / m);
+}
 
 /* ------------------------------------------------------------------------------------------ */
 /* detmath: deterministic fp32 transcendental functions (same operations as ccu_math.cuh)       */

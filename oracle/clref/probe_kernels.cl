@@ -71,3 +71,18 @@ __kernel void probe_math(__global const float* x, __global const float* y, __glo
     }
     out[i] = r;
 }
+
+// vector builtins as the runtime expands them (dot / cross / normalize / length), for the arithmetic contract
+__kernel void probe_vec(__global const float* a, __global const float* b, __global float* out)
+{
+    int i = get_global_id(0);
+    float3 x = vload3(i, a);
+    float3 y = vload3(i, b);
+    float3 c = cross(x, y);
+    float3 n = normalize(x);
+    vstore3(c, i * 3, out);
+    vstore3(n, i * 3 + 1, out);
+    out[i * 9 + 6] = dot(x, y);
+    out[i * 9 + 7] = length(x);
+    out[i * 9 + 8] = 1 / sqrt(dot(x, x));
+}
