@@ -30,6 +30,7 @@ struct DScene {
     const uchar4 *__restrict__ sky;
     int sky_res;
     float sky_intensity;
+    const float *__restrict__ unorm;      // unorm[b] = (float)b / 255.0f
     // sun (Sun_new sky.h:19-40 evaluated once on the device at commit)
     int sun_flags, sun_tex_size, sun_tex;
     float sun_intensity, sun_radius_cos;
@@ -39,18 +40,23 @@ struct DScene {
     float cam[15];
     const float *__restrict__ rays;
     int width, height;
+    float half_width, inv_height;
     // launch parameters
     int draw_depth, max_depth;
     float emitter_scale;
 };
 
+struct Surf {        // what a successful intersection writes into the IntersectionRecord (wavefront.h:37-78)
+    float3 normal;
+    float4 color;
+    float emittance;
+};
+
 struct Record {      // IntersectionRecord, wavefront.h:37-78
     float distance;
     int material;
-    float3 normal;
     float3 point;
-    float4 color;
-    float emittance;
+    Surf surf;
 };
 
 struct HitInfo {     // first-hit bookkeeping, not part of the reference's record
@@ -69,8 +75,10 @@ __device__ __forceinline__ float4 color_from_argb(uint32_t argb) {   // utils.h:
     c.z = (float)(argb & 0xFF) / 256.0f;
     return c;
 }
-__device__ __forceinline__ float4 unorm8(uchar4 t) {
-    return make_float4((float)t.x / 255.0f, (float)t.y / 255.0f, (float)t.z / 255.0f, (float)t.w / 255.0f);
+// RGBA8 UNORM -> float: byte / 255.0f, read from a 256-entry table holding exactly those IEEE quotients
+// (built once on the device by k_unorm_table), which replaces four divisions per texel by four loads.
+__device__ __forceinline__ float4 unorm8(const DScene &s, uchar4 t) {
+    return make_float4(__ldg(s.unorm + t.x), __ldg(s.unorm + t.y), __ldg(s.unorm + t.z), __ldg(s.unorm + t.w));
 }
 // textureAtlas.h:10-16: nearest / clamp-to-edge / integer coordinates
 __device__ __forceinline__ float4 atlas_read_xy(const DScene &s, int x, int y, int location) {
@@ -81,7 +89,7 @@ __device__ __forceinline__ float4 atlas_read_xy(const DScene &s, int x, int y, i
     y = min(max(y, 0), s.atlas_h - 1);
     d = min(max(d, 0), s.atlas_layers - 1);
     size_t tile = ((size_t)d * s.atlas_tiles_y + (y >> 4)) * s.atlas_tiles_x + (x >> 4);
-    return unorm8(__ldg(s.atlas + tile * 256 + ((y & 15) << 4) + (x & 15)));
+    return unorm8(s, __ldg(s.atlas + tile * 256 + ((y & 15) << 4) + (x & 15)));
 }
 // textureAtlas.h:18-28
 __device__ __forceinline__ float4 atlas_read_uv(const DScene &s, float u, float v, int location, int size) {
@@ -110,10 +118,10 @@ __device__ __forceinline__ float4 sky_read(const DScene &s, float cs, float ct) 
     float a, b;
     sky_axis(cs, w, i0, i1, a);
     sky_axis(ct, w, j0, j1, b);
-    float4 t00 = unorm8(__ldg(s.sky + j0 * w + i0));
-    float4 t10 = unorm8(__ldg(s.sky + j0 * w + i1));
-    float4 t01 = unorm8(__ldg(s.sky + j1 * w + i0));
-    float4 t11 = unorm8(__ldg(s.sky + j1 * w + i1));
+    float4 t00 = unorm8(s, __ldg(s.sky + j0 * w + i0));
+    float4 t10 = unorm8(s, __ldg(s.sky + j0 * w + i1));
+    float4 t01 = unorm8(s, __ldg(s.sky + j1 * w + i0));
+    float4 t11 = unorm8(s, __ldg(s.sky + j1 * w + i1));
     float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
     float4 r;
     r.x = ((w00 * t00.x + w10 * t10.x) + w01 * t01.x) + w11 * t11.x;
@@ -126,7 +134,7 @@ __device__ __forceinline__ float4 sky_read(const DScene &s, float cs, float ct) 
 // ------------------------------------------------------------------------------------------------------
 // material.h:31-82
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool material_sample(const DScene &s, int material, Record &rec, float u, float v) {
+__device__ __forceinline__ bool material_sample(const DScene &s, int material, Surf &rec, float u, float v) {
     const int *m = s.mat_palette + material;
     uint32_t flags = __ldg(m), tint = __ldg(m + 1), tex_size = __ldg(m + 2), col = __ldg(m + 3), normal_emittance = __ldg(m + 4);
     float4 color;
@@ -278,8 +286,18 @@ __device__ __forceinline__ float triangle_hit(const int *t, float distance, floa
 // ------------------------------------------------------------------------------------------------------
 // block.h:30-118
 // ------------------------------------------------------------------------------------------------------
-__device__ __noinline__ float intersect_model_block(const DScene &s, int model_type, int model_ptr, Record &rec,
-                                                    float3 norm_origin, float3 direction, float3 inv) {
+struct ModelHit {    // returned by value so that callers keep their state in registers
+    float dist;      // NaN = no hit
+    Surf surf;
+};
+
+// block.h:66-116: AABB models (type 2) and quad models (type 3).  Cold path, kept out of line.
+__device__ __noinline__ ModelHit intersect_model_block(const DScene &s, int model_type, int model_ptr, float3 norm_origin,
+                                                       float3 direction, float3 inv) {
+    ModelHit out;
+    out.surf.normal = f3(0, 0, 0);
+    out.surf.color = make_float4(0, 0, 0, 0);
+    out.surf.emittance = 0;
     float3 normal = f3(0, 0, 0);
     float u = 0, v = 0;
     bool hit = false;
@@ -289,20 +307,24 @@ __device__ __noinline__ float intersect_model_block(const DScene &s, int model_t
         for (int i = 0; i < boxes; i++) {
             int material = 0;
             float t = textured_box(s.aabb_models + model_ptr + 1 + i * 13, dist, norm_origin, direction, inv, normal, u, v, material);
-            if (!is_nan(t) && material_sample(s, material, rec, u, v)) { rec.normal = normal; dist = t; hit = true; }
+            if (!is_nan(t) && material_sample(s, material, out.surf, u, v)) { out.surf.normal = normal; dist = t; hit = true; }
         }
     } else {
         int quads = __ldg(s.quad_models + model_ptr);
         for (int i = 0; i < quads; i++) {
             const int *q = s.quad_models + model_ptr + 1 + i * 15;
             float t = quad_hit(q, dist, norm_origin, direction, normal, u, v);
-            if (!is_nan(t) && material_sample(s, __ldg(q + 13), rec, u, v)) { rec.normal = normal; dist = t; hit = true; }
+            if (!is_nan(t) && material_sample(s, __ldg(q + 13), out.surf, u, v)) { out.surf.normal = normal; dist = t; hit = true; }
         }
     }
-    return hit ? dist : nanf_();
+    out.dist = hit ? dist : nanf_();
+    return out;
 }
 
-__device__ __forceinline__ float intersect_block(const DScene &s, int block, int bx, int by, int bz, Record &rec, float3 pos,
+// Returns the hit distance relative to the marched position (NaN = miss) and fills `surf` on a hit.
+// (The reference also overwrites record.normal when a full block fails its alpha test, block.h:59-60; that
+// value is never read before the next successful hit overwrites it, so it is not reproduced.)
+__device__ __forceinline__ float intersect_block(const DScene &s, int block, int bx, int by, int bz, Surf &surf, float3 pos,
                                                  float3 direction, float3 inv) {
     if (block == CCU_ANY_TYPE) return nanf_();
     if (block < 0 || block + 1 >= s.block_palette_len) return nanf_();   // out-of-palette leaf (undefined in the reference)
@@ -315,10 +337,19 @@ __device__ __forceinline__ float intersect_block(const DScene &s, int block, int
         // the marched position stands in for the direction here, as in block.h:52
         float dist = box_full<false>(unit, norm_origin, pos, inv, normal, u, v);
         if (is_nan(dist)) return nanf_();
-        rec.normal = normal;
-        return material_sample(s, model_ptr, rec, u, v) ? dist - CCU_OFFSET : nanf_();
+        Surf tmp;
+        if (!material_sample(s, model_ptr, tmp, u, v)) return nanf_();
+        surf.color = tmp.color;
+        surf.emittance = tmp.emittance;
+        surf.normal = normal;
+        return dist - CCU_OFFSET;
     }
-    if (model_type == 2 || model_type == 3) return intersect_model_block(s, model_type, model_ptr, rec, norm_origin, direction, inv);
+    if (model_type == 2 || model_type == 3) {
+        ModelHit m = intersect_model_block(s, model_type, model_ptr, norm_origin, direction, inv);
+        if (is_nan(m.dist)) return nanf_();
+        surf = m.surf;
+        return m.dist;
+    }
     return nanf_();
 }
 
@@ -340,53 +371,126 @@ __device__ __forceinline__ int find_leaf(const DScene &s, int bx, int by, int bz
     return -data;
 }
 
-__device__ __forceinline__ bool octree_intersect(const DScene &s, float3 origin, float3 direction, Record &rec, HitInfo &hi) {
+// One ray being marched through the octree (the loop state of octree.h:66-107).
+struct March {
+    float3 o, d, inv;
+    float t;        // distMarch
+    float limit;    // record->distance on entry: +inf for path segments, the surface hit distance for shadow rays
+    int steps;
+};
+
+// octree.h:43-64: returns false when the ray starts outside the octree cube and never enters it
+__device__ __forceinline__ bool march_begin(const DScene &s, March &m, float3 origin, float3 direction, float limit) {
+    m.o = origin;
+    m.d = direction;
+    m.inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+    m.t = 0;
+    m.limit = limit;
+    m.steps = 0;
     const int depth = s.depth;
-    float dist_march = 0;
-    float3 inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
-    float3 offset_d = direction * CCU_OFFSET;
-    {
-        int lx = f2i(floorf(origin.x)) >> depth, ly = f2i(floorf(origin.y)) >> depth, lz = f2i(floorf(origin.z)) >> depth;
-        if ((lx | ly | lz) != 0) {
-            float size = (float)(1 << depth);
-            Box cube = {0, size, 0, size, 0, size};
-            float dist = box_entry(cube, origin, inv);
-            if (is_nan(dist) || dist < 0) return false;
-            dist_march += dist + CCU_OFFSET;
-        }
+    int lx = f2i(floorf(origin.x)) >> depth, ly = f2i(floorf(origin.y)) >> depth, lz = f2i(floorf(origin.z)) >> depth;
+    if ((lx | ly | lz) != 0) {
+        float size = (float)(1 << depth);
+        Box cube = {0, size, 0, size, 0, size};
+        float dist = box_entry(cube, origin, m.inv);
+        if (is_nan(dist) || dist < 0) return false;
+        m.t += dist + CCU_OFFSET;
     }
-    for (int i = 0; i < s.draw_depth; i++) {
-        if (dist_march > rec.distance) return false;
-        float3 pos = origin + direction * dist_march;
-        float3 q = pos + offset_d;
-        int bx = f2i(floorf(q.x)), by = f2i(floorf(q.y)), bz = f2i(floorf(q.z));
-        if (((bx >> depth) | (by >> depth) | (bz >> depth)) != 0) return false;
-        int level, node;
-        int data = find_leaf(s, bx, by, bz, level, node);
-        if (data != 0) {
-            float dist = intersect_block(s, data, bx, by, bz, rec, pos, direction, inv);
-            if (!is_nan(dist)) {
-                rec.distance = dist_march + dist;
-                rec.material = data;
-                hi.node = node;
-                hi.kind = 1;
-                return true;
-            }
-        }
-        int lx = bx >> level, ly = by >> level, lz = bz >> level;
-        Box leaf = {(float)(lx << level), (float)((lx + 1) << level), (float)(ly << level), (float)((ly + 1) << level),
-                    (float)(lz << level), (float)((lz + 1) << level)};
-        dist_march += box_exit(leaf, q, inv) + CCU_OFFSET;
+    return true;
+}
+
+// The voxel the ray is in after marching m.t (octree.h:72-78): position, offset position and block coordinates.
+struct Cell {
+    float3 pos, q;
+    int bx, by, bz;
+};
+__device__ __forceinline__ Cell march_cell(const March &m) {
+    Cell c;
+    c.pos = m.o + m.d * m.t;
+    c.q = c.pos + m.d * CCU_OFFSET;
+    c.bx = f2i(floorf(c.q.x)); c.by = f2i(floorf(c.q.y)); c.bz = f2i(floorf(c.q.z));
+    return c;
+}
+// octree.h:102-106: leave the leaf cube (level `level`) that contains the cell
+__device__ __forceinline__ void march_exit(March &m, const Cell &c, int level) {
+    int lx = c.bx >> level, ly = c.by >> level, lz = c.bz >> level;
+    Box leaf = {(float)(lx << level), (float)((lx + 1) << level), (float)(ly << level), (float)((ly + 1) << level),
+                (float)(lz << level), (float)((lz + 1) << level)};
+    m.t += box_exit(leaf, c.q, m.inv) + CCU_OFFSET;
+    m.steps++;
+}
+// First half of one iteration of octree.h:66-107: locate the leaf under the ray.
+// Returns 0 = air leaf, already left (keep marching); 1 = non-air leaf found (data/level/node set, ray not advanced);
+// 2 = the ray is finished without a hit (step limit, beyond the record's distance, or outside the cube).
+__device__ __forceinline__ int march_probe(const DScene &s, March &m, int &data, int &level, int &node) {
+    if (m.steps >= s.draw_depth || m.t > m.limit) return 2;
+    const int depth = s.depth;
+    Cell c = march_cell(m);
+    if (((c.bx >> depth) | (c.by >> depth) | (c.bz >> depth)) != 0) return 2;
+    data = find_leaf(s, c.bx, c.by, c.bz, level, node);
+    if (data != 0) return 1;   // ray->material is always 0 (wavefront.h:34)
+    march_exit(m, c, level);
+    return 0;
+}
+// Second half: test the non-air leaf found by march_probe.  Returns true on a hit (surf / hit_t filled);
+// otherwise the ray has been advanced past the leaf.
+__device__ __forceinline__ bool march_block(const DScene &s, March &m, int data, int level, Surf &surf, float &hit_t) {
+    Cell c = march_cell(m);
+    float dist = intersect_block(s, data, c.bx, c.by, c.bz, surf, c.pos, m.d, m.inv);
+    if (!is_nan(dist)) {
+        hit_t = m.t + dist;
+        return true;
     }
+    march_exit(m, c, level);
     return false;
+}
+
+// One whole iteration.  Returns 0 = keep marching, 1 = hit (hit_t / surf / block / node filled), 2 = ray left.
+__device__ __forceinline__ int march_step(const DScene &s, March &m, Surf &surf, float &hit_t, int &hit_block, int &hit_node) {
+    int data, level, node;
+    int r = march_probe(s, m, data, level, node);
+    if (r != 1) return r;
+    if (march_block(s, m, data, level, surf, hit_t)) {
+        hit_block = data;
+        hit_node = node;
+        return 1;
+    }
+    return 0;
+}
+
+__device__ __forceinline__ bool octree_intersect(const DScene &s, float3 origin, float3 direction, Record &rec, HitInfo &hi) {
+    March m;
+    if (!march_begin(s, m, origin, direction, rec.distance)) return false;
+    for (;;) {
+        float t;
+        int block, node;
+        int r = march_step(s, m, rec.surf, t, block, node);
+        if (r == 1) {
+            rec.distance = t;
+            rec.material = block;
+            hi.node = node;
+            hi.kind = 1;
+            return true;
+        }
+        if (r == 2) return false;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
 // bvh.h:22-113
 // ------------------------------------------------------------------------------------------------------
-__device__ __noinline__ bool bvh_intersect(const DScene &s, const int *__restrict__ bvh, float3 origin, float3 direction,
-                                           Record &rec, HitInfo &hi, int kind) {
-    bool hit = false;
+struct BvhHit {
+    float dist;      // NaN = no hit closer than `limit`
+    Surf surf;
+};
+
+__device__ __noinline__ BvhHit bvh_intersect(const DScene &s, const int *__restrict__ bvh, float3 origin, float3 direction, float limit) {
+    BvhHit out;
+    out.dist = nanf_();
+    out.surf.normal = f3(0, 0, 0);
+    out.surf.color = make_float4(0, 0, 0, 0);
+    out.surf.emittance = 0;
+    float distance = limit;
     int to_visit = 0, current = 0;
     int stack[64];
     float3 inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
@@ -399,13 +503,11 @@ __device__ __noinline__ bool bvh_intersect(const DScene &s, const int *__restric
                 float3 normal;
                 float u, v;
                 int material;
-                float dist = triangle_hit(s.trigs + prim + 1 + 20 * i, rec.distance, origin, direction, normal, u, v, material);
-                if (!is_nan(dist) && material_sample(s, material, rec, u, v)) {
-                    rec.normal = normal;      // record.material keeps its octree value (bvh.h:59-65)
-                    rec.distance = dist;
-                    hit = true;
-                    hi.kind = kind;
-                    hi.node = -1;
+                float dist = triangle_hit(s.trigs + prim + 1 + 20 * i, distance, origin, direction, normal, u, v, material);
+                if (!is_nan(dist) && material_sample(s, material, out.surf, u, v)) {
+                    out.surf.normal = normal;      // record.material keeps its octree value (bvh.h:59-65)
+                    distance = dist;
+                    out.dist = dist;
                 }
             }
             if (to_visit == 0) break;
@@ -418,8 +520,8 @@ __device__ __noinline__ bool bvh_intersect(const DScene &s, const int *__restric
             Box b2 = {i2f(__ldg(n2 + 1)), i2f(__ldg(n2 + 2)), i2f(__ldg(n2 + 3)), i2f(__ldg(n2 + 4)), i2f(__ldg(n2 + 5)), i2f(__ldg(n2 + 6))};
             float t1 = box_entry(b1, origin, inv);
             float t2 = box_entry(b2, origin, inv);
-            bool miss1 = is_nan(t1) || t1 > rec.distance;
-            bool miss2 = is_nan(t2) || t2 > rec.distance;
+            bool miss1 = is_nan(t1) || t1 > distance;
+            bool miss2 = is_nan(t2) || t2 > distance;
             if (miss1) {
                 if (miss2) {
                     if (to_visit == 0) break;
@@ -438,14 +540,32 @@ __device__ __noinline__ bool bvh_intersect(const DScene &s, const int *__restric
             }
         }
     }
+    return out;
+}
+
+// The two BVH probes of kernel.h:17-18 applied to a record whose octree part is already resolved.
+__device__ __forceinline__ bool bvh_pair(const DScene &s, float3 origin, float3 direction, float &distance, Surf &surf, int &kind) {
+    bool hit = false;
+    if (!s.world_bvh_empty) {
+        BvhHit h = bvh_intersect(s, s.world_bvh, origin, direction, distance);
+        if (!is_nan(h.dist)) { distance = h.dist; surf = h.surf; hit = true; kind = 2; }
+    }
+    if (!s.actor_bvh_empty) {
+        BvhHit h = bvh_intersect(s, s.actor_bvh, origin, direction, distance);
+        if (!is_nan(h.dist)) { distance = h.dist; surf = h.surf; hit = true; kind = 3; }
+    }
     return hit;
 }
 
 // kernel.h:14-24
 __device__ __forceinline__ bool closest_intersect(const DScene &s, float3 origin, float3 direction, Record &rec, HitInfo &hi) {
     bool hit = octree_intersect(s, origin, direction, rec, hi);
-    if (!s.world_bvh_empty) hit |= bvh_intersect(s, s.world_bvh, origin, direction, rec, hi, 2);
-    if (!s.actor_bvh_empty) hit |= bvh_intersect(s, s.actor_bvh, origin, direction, rec, hi, 3);
+    int kind = 0;
+    if (bvh_pair(s, origin, direction, rec.distance, rec.surf, kind)) {
+        hit = true;
+        hi.kind = kind;
+        hi.node = -1;
+    }
     if (hit) rec.point = origin + direction * (rec.distance - CCU_OFFSET);
     return hit;
 }
@@ -453,11 +573,14 @@ __device__ __forceinline__ bool closest_intersect(const DScene &s, float3 origin
 // ------------------------------------------------------------------------------------------------------
 // sky.h / kernel.h shading
 // ------------------------------------------------------------------------------------------------------
-// sky.h:97-106 + sky.h:42-66, then the accumulation of kernel.h:26-31
+// sky.h:97-106 + sky.h:42-66: radiance seen along a ray that left the scene (sky texel x intensity + sun disc)
 __device__ __forceinline__ float3 sky_radiance(const DScene &s, float3 d) {
     float theta = dm_atan2(d.z, d.x);
     theta /= CCU_PI_F * 2;
-    theta = fmodf(fmodf(theta, 1.0f) + 1.0f, 1.0f);
+    // fmod(x, 1) == x - trunc(x) exactly for every float (inf -> NaN, NaN -> NaN): sky.h:100 without the libm loop
+    theta = theta - truncf(theta);
+    theta = theta + 1.0f;
+    theta = theta - truncf(theta);
     float phi = (dm_asin(fminf(fmaxf(d.y, -1.0f), 1.0f)) + CCU_PI_2_F) * CCU_INV_PI_F;
     float4 sky = sky_read(s, theta, phi);
     float3 col = f3(sky.x * s.sky_intensity, sky.y * s.sky_intensity, sky.z * s.sky_intensity);
@@ -479,21 +602,17 @@ __device__ __forceinline__ float3 sky_radiance(const DScene &s, float3 d) {
     return col;
 }
 
-struct PathState {
-    float3 origin, direction;
-    float3 color, throughput;
-    uint32_t rng;
-    int ray_depth;
-};
-
 // camera.h:8-32 + rayTracer.cl:55-91 (NORMALIZE = preview variant, rayTracer.cl:186)
 template <bool NORMALIZE>
 __device__ __forceinline__ void camera_ray(const DScene &s, int gid, uint32_t &rng, float3 &origin, float3 &direction) {
     if (s.projector_type != -1) {
-        float half_width = (float)(s.width / (2.0 * s.height));
-        float inv_height = (float)(1.0 / s.height);
-        float x = -half_width + ((float)(gid % s.width) + rng_float(rng)) * inv_height;
-        float y = (float)(-0.5 + (double)(((float)(gid / s.width) + rng_float(rng)) * inv_height));
+        // half_width = (float)(W / (2.0 * H)), inv_height = (float)(1.0 / H): the double expressions of
+        // rayTracer.cl:66-67, evaluated once on the host (IEEE doubles, identical on any machine)
+        const float half_width = s.half_width, inv_height = s.inv_height;
+        int py = gid / s.width;
+        int px = gid - py * s.width;
+        float x = -half_width + ((float)px + rng_float(rng)) * inv_height;
+        float y = (float)(-0.5 + (double)(((float)py + rng_float(rng)) * inv_height));
         float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
         if (s.projector_type == 0) {
             float aperture = s.cam[12], subject_distance = s.cam[13], fov_tan = s.cam[14];
@@ -520,86 +639,91 @@ __device__ __forceinline__ void camera_ray(const DScene &s, int gid, uint32_t &r
     }
 }
 
-// one path sample for pixel gid: rayTracer.cl:40-107 (+ kernel.h:33-98, sky.h:68-93)
+// sky.h:68-93: direction towards the sun disc; x1, x2 are the two RNG draws (component-wise product u*v)
+__device__ __forceinline__ float3 sun_sample_direction(const DScene &s, float x1, float x2) {
+    float cos_a = 1 - x1 + x1 * s.sun_radius_cos;
+    float sin_a = sqrtf(1 - cos_a * cos_a);
+    float phi = 2 * CCU_PI_F * x2;
+    float sn, cs;
+    dm_sincos(phi, sn, cs);
+    float3 u = s.su * (cs * sin_a);
+    float3 v = s.sv * (sn * sin_a);
+    float3 w = s.sw * cos_a;
+    return normalize3((u * v) + w);
+}
+
+// kernel.h:50-92: cosine-weighted diffuse bounce direction around normal n; x1, x2 are the two RNG draws
+__device__ __forceinline__ float3 diffuse_direction(float3 n, float x1, float x2) {
+    float r = sqrtf(x1);
+    float theta = 2 * CCU_PI_F * x2;
+    float sn, cs;
+    dm_sincos(theta, sn, cs);
+    float tx = r * cs, ty = r * sn;
+    float tz = sqrtf(1 - x1);
+    float xx, xy, xz = 0;
+    if ((double)fabsf(n.x) > 0.1) { xx = 0; xy = 1; } else { xx = 1; xy = 0; }
+    float ux = xy * n.z - xz * n.y;
+    float uy = xz * n.x - xx * n.z;
+    float uz = xx * n.y - xy * n.x;
+    r = 1 / sqrtf((ux * ux + uy * uy) + uz * uz);
+    ux *= r; uy *= r; uz *= r;
+    float vx = uy * n.z - uz * n.y;
+    float vy = uz * n.x - ux * n.z;
+    float vz = ux * n.y - uy * n.x;
+    return f3((ux * tx + vx * ty) + n.x * tz, (uy * tx + vy * ty) + n.y * tz, (uz * tx + vz * ty) + n.z * tz);
+}
+
+// one path sample for pixel gid, thread-sequential: rayTracer.cl:40-107 (+ kernel.h:33-98, sky.h:68-93)
 __device__ __forceinline__ float3 sample_pixel(const DScene &s, int gid, int seed) {
-    PathState p;
-    p.color = f3(0, 0, 0);
-    p.throughput = f3(1, 1, 1);
-    p.ray_depth = 0;
-    p.rng = (uint32_t)seed + (uint32_t)gid;
-    rng_next(p.rng);
-    camera_ray<false>(s, gid, p.rng, p.origin, p.direction);
+    float3 color = f3(0, 0, 0), throughput = f3(1, 1, 1);
+    int ray_depth = 0;
+    uint32_t rng = (uint32_t)seed + (uint32_t)gid;
+    rng_next(rng);
+    float3 origin, direction;
+    camera_ray<false>(s, gid, rng, origin, direction);
     Record rec;
     rec.distance = inff_();
     rec.material = 0;
-    rec.normal = f3(0, 0, 0);
     rec.point = f3(0, 0, 0);
-    rec.color = make_float4(0, 0, 0, 0);
-    rec.emittance = 0;
+    rec.surf.normal = f3(0, 0, 0);
+    rec.surf.color = make_float4(0, 0, 0, 0);
+    rec.surf.emittance = 0;
     HitInfo hi = {-1, 0};
     for (;;) {
-        if (!closest_intersect(s, p.origin, p.direction, rec, hi)) {
+        if (!closest_intersect(s, origin, direction, rec, hi)) {
             // miss: emittance = 1, sky (+ sun disc) added through the throughput (rayTracer.cl:95-97, kernel.h:26-31)
-            float3 sky = sky_radiance(s, p.direction);
-            p.color = p.color + (sky * p.throughput) * 1.0f;
+            float3 sky = sky_radiance(s, direction);
+            color = color + (sky * throughput) * 1.0f;
             break;
         }
         // kernel.h:33-44
-        p.origin = rec.point;
-        float3 col = f3(rec.color.x, rec.color.y, rec.color.z);
-        p.throughput = p.throughput * col;
-        p.color = p.color + (col * (rec.emittance * s.emitter_scale)) * p.throughput;
+        origin = rec.point;
+        float3 col = f3(rec.surf.color.x, rec.surf.color.y, rec.surf.color.z);
+        throughput = throughput * col;
+        color = color + (col * (rec.surf.emittance * s.emitter_scale)) * throughput;
         // sun sampling + shadow ray (sky.h:68-93, rayTracer.cl:101-106)
         if (s.sun_flags & 1) {
-            float x1 = rng_float(p.rng);
-            float x2 = rng_float(p.rng);
-            float cos_a = 1 - x1 + x1 * s.sun_radius_cos;
-            float sin_a = sqrtf(1 - cos_a * cos_a);
-            float phi = 2 * CCU_PI_F * x2;
-            float sn, cs;
-            dm_sincos(phi, sn, cs);
-            float3 u = s.su * (cs * sin_a);
-            float3 v = s.sv * (sn * sin_a);
-            float3 w = s.sw * cos_a;
-            float3 d = normalize3((u * v) + w);      // component-wise product, as the reference
-            p.direction = d;
-            float shadow_emittance = fabsf(dot3(d, rec.normal));
+            float x1 = rng_float(rng);
+            float x2 = rng_float(rng);
+            float3 d = sun_sample_direction(s, x1, x2);
+            float shadow_emittance = fabsf(dot3(d, rec.surf.normal));
             Record sh = rec;                          // keeps the surface hit's distance as the ray limit
             HitInfo shi;
-            if (!closest_intersect(s, p.origin, d, sh, shi)) {
+            if (!closest_intersect(s, origin, d, sh, shi)) {
                 float3 sky = sky_radiance(s, d);
-                p.color = p.color + (sky * p.throughput) * shadow_emittance;
+                color = color + (sky * throughput) * shadow_emittance;
             }
         }
         // kernel.h:46-98 diffuse bounce
-        {
-            float x1 = rng_float(p.rng);
-            float x2 = rng_float(p.rng);
-            float r = sqrtf(x1);
-            float theta = 2 * CCU_PI_F * x2;
-            float sn, cs;
-            dm_sincos(theta, sn, cs);
-            float tx = r * cs, ty = r * sn;
-            float tz = sqrtf(1 - x1);
-            float3 n = rec.normal;
-            float xx, xy, xz = 0;
-            if ((double)fabsf(n.x) > 0.1) { xx = 0; xy = 1; } else { xx = 1; xy = 0; }
-            float ux = xy * n.z - xz * n.y;
-            float uy = xz * n.x - xx * n.z;
-            float uz = xx * n.y - xy * n.x;
-            r = 1 / sqrtf((ux * ux + uy * uy) + uz * uz);
-            ux *= r; uy *= r; uz *= r;
-            float vx = uy * n.z - uz * n.y;
-            float vy = uz * n.x - ux * n.z;
-            float vz = ux * n.y - uy * n.x;
-            p.direction = f3((ux * tx + vx * ty) + n.x * tz, (uy * tx + vy * ty) + n.y * tz, (uz * tx + vz * ty) + n.z * tz);
-            p.origin = rec.point + p.direction * CCU_OFFSET;
-            p.ray_depth += 1;
-            rec.distance = inff_();
-            if (!(p.ray_depth < s.max_depth)) break;
-        }
+        float x1 = rng_float(rng);
+        float x2 = rng_float(rng);
+        direction = diffuse_direction(rec.surf.normal, x1, x2);
+        origin = rec.point + direction * CCU_OFFSET;
+        ray_depth += 1;
+        rec.distance = inff_();
+        if (!(ray_depth < s.max_depth)) break;
     }
-    return p.color;
+    return color;
 }
 
 }  // namespace ccu

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -13,6 +14,7 @@
 
 #include "../../include/chunkycu.h"
 #include "ccu_device.cuh"
+#include "ccu_wavefront.cuh"
 
 using namespace ccu;
 
@@ -72,22 +74,22 @@ __global__ void __launch_bounds__(128) k_first_hit(const __grid_constant__ DScen
     float3 o, d;
     camera_ray<false>(s, gid, rng, o, d);
     Record rec;
-    rec.distance = inff_(); rec.material = 0; rec.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
-    rec.color = make_float4(0, 0, 0, 0); rec.emittance = 0;
+    rec.distance = inff_(); rec.material = 0; rec.surf.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
+    rec.surf.color = make_float4(0, 0, 0, 0); rec.surf.emittance = 0;
     HitInfo hi = {-1, 0};
     bool hit = closest_intersect(s, o, d, rec, hi);
     if (block) block[gid] = hit ? rec.material : 0;
-    if (face) face[gid] = hit ? face_of(rec.normal) : 6;
+    if (face) face[gid] = hit ? face_of(rec.surf.normal) : 6;
     if (node) node[gid] = hit ? hi.node : -1;
     if (kind) kind[gid] = hit ? hi.kind : 0;
     if (t) t[gid] = hit ? rec.distance : inff_();
     if (normal) {
-        normal[gid * 3 + 0] = hit ? rec.normal.x : 0.0f;
-        normal[gid * 3 + 1] = hit ? rec.normal.y : 0.0f;
-        normal[gid * 3 + 2] = hit ? rec.normal.z : 0.0f;
+        normal[gid * 3 + 0] = hit ? rec.surf.normal.x : 0.0f;
+        normal[gid * 3 + 1] = hit ? rec.surf.normal.y : 0.0f;
+        normal[gid * 3 + 2] = hit ? rec.surf.normal.z : 0.0f;
     }
     if (color) {
-        float4 c = hit ? rec.color : make_float4(0, 0, 0, 0);
+        float4 c = hit ? rec.surf.color : make_float4(0, 0, 0, 0);
         reinterpret_cast<float4 *>(color)[gid] = c;
     }
 }
@@ -107,14 +109,14 @@ __global__ void __launch_bounds__(128) k_preview(const __grid_constant__ DScene 
     float3 o, d;
     camera_ray<true>(s, gid, rng, o, d);
     Record rec;
-    rec.distance = inff_(); rec.material = 0; rec.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
-    rec.color = make_float4(0, 0, 0, 0); rec.emittance = 0;
+    rec.distance = inff_(); rec.material = 0; rec.surf.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
+    rec.surf.color = make_float4(0, 0, 0, 0); rec.surf.emittance = 0;
     HitInfo hi = {-1, 0};
     float3 c;
     if (closest_intersect(s, o, d, rec, hi)) {
-        float shading = dot3(rec.normal, f3(0.25f, 0.866f, 0.433f));
+        float shading = dot3(rec.surf.normal, f3(0.25f, 0.866f, 0.433f));
         shading = fmaxf(0.3f, shading);
-        c = f3(rec.color.x * shading, rec.color.y * shading, rec.color.z * shading);
+        c = f3(rec.surf.color.x * shading, rec.surf.color.y * shading, rec.surf.color.z * shading);
     } else {
         c = sky_radiance(s, d);
     }
@@ -127,6 +129,8 @@ __global__ void __launch_bounds__(128) k_preview(const __grid_constant__ DScene 
     }
     res[gid] = (int)(0xFF000000u | ((uint32_t)rgb[0] << 16) | ((uint32_t)rgb[1] << 8) | (uint32_t)rgb[2]);
 }
+
+__global__ void k_unorm_table(float *t) { t[threadIdx.x] = (float)threadIdx.x / 255.0f; }
 
 __global__ void k_scale(float *buf, float factor, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] *= factor;
@@ -205,6 +209,7 @@ struct ccu_ctx {
     bool have_sun = false;
     bool committed = false;
     DevBuf<float> sun_basis;
+    float *unorm = nullptr;
 
     // camera
     int projector_type = 0;
@@ -217,6 +222,9 @@ struct ccu_ctx {
     float *accum = nullptr;      // running mean float[3*W*H]
     float *pinned = nullptr;     // host staging float[3*W*H]
     int *seeds_dev = nullptr;
+    unsigned int *work_counter = nullptr;
+    int wait_lanes = 8;
+    int blocks_per_sm = 2;
     int seeds_cap = 0;
     int window_spp = 0;
     bool target_live = false;    // between ccu_render_begin and ccu_render_end
@@ -274,12 +282,17 @@ int fill_scene(ccu_ctx *c) {
     s.sky = c->sky.p;
     s.sky_res = c->sky_res;
     s.sky_intensity = c->sky_intensity;
+    s.unorm = c->unorm;
     s.sun_flags = c->sun_host[0]; s.sun_tex_size = c->sun_host[1]; s.sun_tex = c->sun_host[2];
     memcpy(&s.sun_intensity, &c->sun_host[3], 4);
     s.projector_type = c->projector_type;
     memcpy(s.cam, c->cam, sizeof s.cam);
     s.rays = c->rays.p;
     s.width = c->width; s.height = c->height;
+    if (c->height > 0) {
+        s.half_width = (float)(c->width / (2.0 * c->height));   // rayTracer.cl:66
+        s.inv_height = (float)(1.0 / c->height);                // rayTracer.cl:67
+    }
     s.draw_depth = c->params.draw_depth; s.max_depth = c->params.max_depth; s.emitter_scale = c->params.emitter_scale;
     return CCU_OK;
 }
@@ -353,10 +366,18 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     ccu_ctx *c = new ccu_ctx();
     c->device = device_index;
     c->sm_count = p.multiProcessorCount;
+    if (const char *e = getenv("CCU_WAIT_LANES")) c->wait_lanes = std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("CCU_BLOCKS_PER_SM")) c->blocks_per_sm = std::max(1, std::min(8, atoi(e)));
     DeviceGuard g(device_index);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaMalloc(&c->unorm, 256 * sizeof(float));
+    if (e == cudaSuccess) {
+        k_unorm_table<<<1, 256, 0, c->stream>>>(c->unorm);
+        c->launches++;
+        e = cudaStreamSynchronize(c->stream);
+    }
     if (e != cudaSuccess) {
         delete c;
         return fail(CCU_ECUDA, "context setup: %s", cudaGetErrorString(e));
@@ -379,6 +400,8 @@ int ccu_ctx_destroy(ccu_ctx *c) {
         if (c->accum) cudaFree(c->accum);
         if (c->pinned) cudaFreeHost(c->pinned);
         if (c->seeds_dev) cudaFree(c->seeds_dev);
+        if (c->work_counter) cudaFree(c->work_counter);
+        if (c->unorm) cudaFree(c->unorm);
         cudaEventDestroy(c->ev0);
         cudaEventDestroy(c->ev1);
         cudaStreamDestroy(c->stream);
@@ -618,11 +641,29 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
     CU(cudaStreamSynchronize(c->stream));   // seeds[] belongs to the caller again
     fill_scene(c);
     int n_pixels = c->width * c->height;
+    if (!c->work_counter) CU(cudaMalloc(&c->work_counter, sizeof(unsigned int)));
     CU(cudaEventRecord(c->ev0, c->stream));
-    {
+    if (c->params.kernel != 1) CU(cudaMemsetAsync(c->work_counter, 0, sizeof(unsigned int), c->stream));
+    if (c->params.kernel == 1) {
         int threads = 128;
         int blocks = (n_pixels + threads - 1) / threads;
         k_render_mega<<<blocks, threads, 0, c->stream>>>(c->scene, c->seeds_dev, n_passes, c->window_spp, c->accum, n_pixels);
+        c->launches++;
+    } else {
+        // persistent wavefront kernel: one resident grid, pixels handed out through a counter
+        WaveParams wp;
+        wp.seeds = c->seeds_dev;
+        wp.n_passes = n_passes;
+        wp.start_spp = c->window_spp;
+        wp.res = c->accum;
+        wp.n_pixels = n_pixels;
+        wp.next_pixel = c->work_counter;
+        wp.wait_lanes = c->wait_lanes;
+        int blocks = c->sm_count * c->blocks_per_sm;
+        if (c->scene.world_bvh_empty && c->scene.actor_bvh_empty)
+            k_render_wave<false><<<blocks, 256, 0, c->stream>>>(c->scene, wp);
+        else
+            k_render_wave<true><<<blocks, 256, 0, c->stream>>>(c->scene, wp);
         c->launches++;
     }
     CU(cudaGetLastError());

@@ -33,14 +33,20 @@ def test_first_hit_bit_exact(name, scenes, cuda_ctx):
     assert (ref["kind"] > 0).any()
 
 
+@pytest.mark.parametrize("kernel", [2, 1], ids=["wavefront", "megakernel"])
 @pytest.mark.parametrize("name", ALL)
-def test_render_bit_exact(name, scenes, cuda_ctx):
+def test_render_bit_exact(name, kernel, scenes, cuda_ctx):
+    """Both render kernels (persistent wavefront = default, thread-per-pixel megakernel) against the oracle."""
     import oracle
     p = scenes(name)
     load_scene(cuda_ctx, p)
-    seeds = pass_seeds(6)
-    cuda_ctx.render_passes(seeds)
-    got, spp = cuda_ctx.render_read()
+    cuda_ctx.render_set_params(kernel=kernel)
+    try:
+        seeds = pass_seeds(6)
+        cuda_ctx.render_passes(seeds)
+        got, spp = cuda_ctx.render_read()
+    finally:
+        cuda_ctx.render_set_params()
     assert spp == 6
     ref = oracle.Oracle(p).render(seeds)
     bad = _bits(got) != _bits(ref)
