@@ -13,6 +13,15 @@ struct DScene {
     // octree (reference numbering: ClSceneLoader.java:56-59)
     const int *__restrict__ tree;
     int depth;
+    // traversal layout built at commit (result-identical to the root descent of octree.h:81-88):
+    //   top[]   dense table over the cells of level `cell_level` (edge 1 << cell_level), index (x*dim + y)*dim + z
+    //   wide[]  64-ary nodes, each covering two octree levels: entry ((x&3)<<4 | (y&3)<<2 | (z&3)) at the node's level
+    // entry encoding: bit 31 set = leaf {level: bits 30..26, value: bits 25..0 (0x3FFFFFF = ANY_TYPE)};
+    //                 bit 31 clear = index of a wide node (in units of 64 words)
+    const unsigned *__restrict__ top;
+    const unsigned *__restrict__ wide;
+    int cell_level, top_log2;
+    int use_wide;
     // palettes (reference packed layouts)
     const int *__restrict__ block_palette;
     int block_palette_len;
@@ -371,6 +380,23 @@ __device__ __forceinline__ int find_leaf(const DScene &s, int bx, int by, int bz
     return -data;
 }
 
+#define CCU_WIDE_LEAF 0x80000000u
+#define CCU_WIDE_ANY 0x3FFFFFFu
+// Same answer as find_leaf (leaf value and level) from the commit-time layout: one table lookup plus one load per
+// two octree levels below the table's cell level.
+__device__ __forceinline__ int find_leaf_wide(const DScene &s, int bx, int by, int bz, int &level) {
+    const int cl = s.cell_level;
+    unsigned e = __ldg(s.top + ((((bx >> cl) << s.top_log2) + (by >> cl)) << s.top_log2) + (bz >> cl));
+    int lvl = cl;
+    while (!(e & CCU_WIDE_LEAF)) {
+        lvl -= 2;
+        e = __ldg(s.wide + (size_t)e * 64 + ((((bx >> lvl) & 3) << 4) | (((by >> lvl) & 3) << 2) | ((bz >> lvl) & 3)));
+    }
+    level = (e >> 26) & 31;
+    unsigned v = e & CCU_WIDE_ANY;
+    return v == CCU_WIDE_ANY ? CCU_ANY_TYPE : (int)v;
+}
+
 // One ray being marched through the octree (the loop state of octree.h:66-107).
 struct March {
     float3 o, d, inv;
@@ -422,12 +448,14 @@ __device__ __forceinline__ void march_exit(March &m, const Cell &c, int level) {
 // First half of one iteration of octree.h:66-107: locate the leaf under the ray.
 // Returns 0 = air leaf, already left (keep marching); 1 = non-air leaf found (data/level/node set, ray not advanced);
 // 2 = the ray is finished without a hit (step limit, beyond the record's distance, or outside the cube).
+template <bool WIDE>
 __device__ __forceinline__ int march_probe(const DScene &s, March &m, int &data, int &level, int &node) {
     if (m.steps >= s.draw_depth || m.t > m.limit) return 2;
     const int depth = s.depth;
     Cell c = march_cell(m);
     if (((c.bx >> depth) | (c.by >> depth) | (c.bz >> depth)) != 0) return 2;
-    data = find_leaf(s, c.bx, c.by, c.bz, level, node);
+    if (WIDE) { data = find_leaf_wide(s, c.bx, c.by, c.bz, level); node = -1; }
+    else data = find_leaf(s, c.bx, c.by, c.bz, level, node);
     if (data != 0) return 1;   // ray->material is always 0 (wavefront.h:34)
     march_exit(m, c, level);
     return 0;
@@ -446,9 +474,10 @@ __device__ __forceinline__ bool march_block(const DScene &s, March &m, int data,
 }
 
 // One whole iteration.  Returns 0 = keep marching, 1 = hit (hit_t / surf / block / node filled), 2 = ray left.
+template <bool WIDE>
 __device__ __forceinline__ int march_step(const DScene &s, March &m, Surf &surf, float &hit_t, int &hit_block, int &hit_node) {
     int data, level, node;
-    int r = march_probe(s, m, data, level, node);
+    int r = march_probe<WIDE>(s, m, data, level, node);
     if (r != 1) return r;
     if (march_block(s, m, data, level, surf, hit_t)) {
         hit_block = data;
@@ -458,13 +487,14 @@ __device__ __forceinline__ int march_step(const DScene &s, March &m, Surf &surf,
     return 0;
 }
 
+template <bool WIDE>
 __device__ __forceinline__ bool octree_intersect(const DScene &s, float3 origin, float3 direction, Record &rec, HitInfo &hi) {
     March m;
     if (!march_begin(s, m, origin, direction, rec.distance)) return false;
     for (;;) {
         float t;
         int block, node;
-        int r = march_step(s, m, rec.surf, t, block, node);
+        int r = march_step<WIDE>(s, m, rec.surf, t, block, node);
         if (r == 1) {
             rec.distance = t;
             rec.material = block;
@@ -558,8 +588,9 @@ __device__ __forceinline__ bool bvh_pair(const DScene &s, float3 origin, float3 
 }
 
 // kernel.h:14-24
+template <bool WIDE>
 __device__ __forceinline__ bool closest_intersect(const DScene &s, float3 origin, float3 direction, Record &rec, HitInfo &hi) {
-    bool hit = octree_intersect(s, origin, direction, rec, hi);
+    bool hit = octree_intersect<WIDE>(s, origin, direction, rec, hi);
     int kind = 0;
     if (bvh_pair(s, origin, direction, rec.distance, rec.surf, kind)) {
         hit = true;
@@ -674,6 +705,7 @@ __device__ __forceinline__ float3 diffuse_direction(float3 n, float x1, float x2
 }
 
 // one path sample for pixel gid, thread-sequential: rayTracer.cl:40-107 (+ kernel.h:33-98, sky.h:68-93)
+template <bool WIDE>
 __device__ __forceinline__ float3 sample_pixel(const DScene &s, int gid, int seed) {
     float3 color = f3(0, 0, 0), throughput = f3(1, 1, 1);
     int ray_depth = 0;
@@ -690,7 +722,7 @@ __device__ __forceinline__ float3 sample_pixel(const DScene &s, int gid, int see
     rec.surf.emittance = 0;
     HitInfo hi = {-1, 0};
     for (;;) {
-        if (!closest_intersect(s, origin, direction, rec, hi)) {
+        if (!closest_intersect<WIDE>(s, origin, direction, rec, hi)) {
             // miss: emittance = 1, sky (+ sun disc) added through the throughput (rayTracer.cl:95-97, kernel.h:26-31)
             float3 sky = sky_radiance(s, direction);
             color = color + (sky * throughput) * 1.0f;
@@ -709,7 +741,7 @@ __device__ __forceinline__ float3 sample_pixel(const DScene &s, int gid, int see
             float shadow_emittance = fabsf(dot3(d, rec.surf.normal));
             Record sh = rec;                          // keeps the surface hit's distance as the ray limit
             HitInfo shi;
-            if (!closest_intersect(s, origin, d, sh, shi)) {
+            if (!closest_intersect<WIDE>(s, origin, d, sh, shi)) {
                 float3 sky = sky_radiance(s, d);
                 color = color + (sky * throughput) * shadow_emittance;
             }

@@ -34,7 +34,7 @@ struct WaveParams {
     int wait_lanes;             // leave the march loop once this many lanes of the warp are waiting
 };
 
-template <bool HAS_BVH>
+template <bool HAS_BVH, bool WIDE>
 __global__ void __launch_bounds__(256, 2) k_render_wave(const __grid_constant__ DScene s, const __grid_constant__ WaveParams w) {
     const unsigned full = 0xffffffffu;
     // pixel / pass
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256, 2) k_render_wave(const __grid_constant__ 
         for (;;) {
             if (state == LS_MARCH) {
                 int node;
-                int r = march_probe(s, m, leaf_data, leaf_level, node);
+                int r = march_probe<WIDE>(s, m, leaf_data, leaf_level, node);
                 if (r == 1) state = LS_BLOCK;
                 else if (r == 2) { ray_hit = false; state = LS_RAY_DONE; }
             }

@@ -15,6 +15,7 @@
 #include "../../include/chunkycu.h"
 #include "ccu_device.cuh"
 #include "ccu_wavefront.cuh"
+#include "ccu_pool.cuh"
 
 using namespace ccu;
 
@@ -38,13 +39,14 @@ __global__ void k_sun_setup(const int *sun_words, float *out /* su sv sw radius_
 
 // Thread-per-pixel path tracer: all passes of the batch in one launch, the running mean of
 // rayTracer.cl:109-112 carried in registers between passes (identical arithmetic, no memory round trip).
+template <bool WIDE>
 __global__ void __launch_bounds__(128) k_render_mega(const __grid_constant__ DScene s, const int *__restrict__ seeds, int n_passes,
                                                      int start_spp, float *__restrict__ res, int n_pixels) {
     for (int gid = blockIdx.x * blockDim.x + threadIdx.x; gid < n_pixels; gid += gridDim.x * blockDim.x) {
         float *px = res + (size_t)gid * 3;
         float3 buf = f3(px[0], px[1], px[2]);
         for (int pass = 0; pass < n_passes; pass++) {
-            float3 col = sample_pixel(s, gid, __ldg(seeds + pass));
+            float3 col = sample_pixel<WIDE>(s, gid, __ldg(seeds + pass));
             int spp = start_spp + pass;
             float fs = (float)spp, fs1 = (float)(spp + 1);
             buf.x = (buf.x * fs + col.x) / fs1;
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(128) k_first_hit(const __grid_constant__ DScen
     rec.distance = inff_(); rec.material = 0; rec.surf.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
     rec.surf.color = make_float4(0, 0, 0, 0); rec.surf.emittance = 0;
     HitInfo hi = {-1, 0};
-    bool hit = closest_intersect(s, o, d, rec, hi);
+    bool hit = closest_intersect<false>(s, o, d, rec, hi);   // reference layout: reports the leaf's treeData index
     if (block) block[gid] = hit ? rec.material : 0;
     if (face) face[gid] = hit ? face_of(rec.surf.normal) : 6;
     if (node) node[gid] = hit ? hi.node : -1;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(128) k_preview(const __grid_constant__ DScene 
     rec.surf.color = make_float4(0, 0, 0, 0); rec.surf.emittance = 0;
     HitInfo hi = {-1, 0};
     float3 c;
-    if (closest_intersect(s, o, d, rec, hi)) {
+    if (closest_intersect<false>(s, o, d, rec, hi)) {
         float shading = dot3(rec.surf.normal, f3(0.25f, 0.866f, 0.433f));
         shading = fmaxf(0.3f, shading);
         c = f3(rec.surf.color.x * shading, rec.surf.color.y * shading, rec.surf.color.z * shading);
@@ -202,6 +204,9 @@ struct ccu_ctx {
     DevBuf<int> tree, block_palette, quad_models, aabb_models, mat_palette, trigs, world_bvh, actor_bvh, sun_words;
     std::vector<int> world_head, actor_head;    // first node of each BVH for the emptiness probe
     DevBuf<uchar4> atlas, sky;
+    std::vector<int> tree_host;              // kept for the commit-time traversal layout
+    DevBuf<unsigned> top, wide;
+    int cell_level = 0, top_log2 = 0, use_wide = 0;
     int atlas_w = 0, atlas_h = 0, atlas_layers = 0;
     int depth = 0, sky_res = 0;
     float sky_intensity = 0;
@@ -223,7 +228,9 @@ struct ccu_ctx {
     float *pinned = nullptr;     // host staging float[3*W*H]
     int *seeds_dev = nullptr;
     unsigned int *work_counter = nullptr;
-    int wait_lanes = 8;
+    int wait_lanes = 24;
+    int refill_min = 4;
+    int exit_idle = 8;
     int blocks_per_sm = 2;
     int seeds_cap = 0;
     int window_spp = 0;
@@ -266,6 +273,11 @@ int fill_scene(ccu_ctx *c) {
     DScene &s = c->scene;
     s.tree = c->tree.p;
     s.depth = c->depth;
+    s.top = c->top.p;
+    s.wide = c->wide.p;
+    s.cell_level = c->cell_level;
+    s.top_log2 = c->top_log2;
+    s.use_wide = c->use_wide;
     s.block_palette = c->block_palette.p;
     s.block_palette_len = (int)c->block_palette.n;
     s.quad_models = c->quad_models.p;
@@ -315,6 +327,78 @@ void stop_timer(ccu_ctx *c) {
     }
 }
 
+}  // namespace
+
+
+// ------------------------------------------------------------------------------------------------------
+// commit-time traversal layout (see DScene::top / DScene::wide)
+// ------------------------------------------------------------------------------------------------------
+namespace {
+struct WideLayout {
+    std::vector<unsigned> top, wide;
+    int cell_level = 0, top_log2 = 0;
+    bool ok = true;
+};
+
+inline unsigned wide_leaf(int word, int level, bool &ok) {
+    long long v = -(long long)word;
+    unsigned val;
+    if (v == 0x7FFFFFFELL) val = CCU_WIDE_ANY;
+    else if (v >= 0 && v < (long long)CCU_WIDE_ANY) val = (unsigned)v;
+    else { ok = false; val = 0; }
+    return CCU_WIDE_LEAF | ((unsigned)level << 26) | val;
+}
+
+unsigned wide_node(const int *tree, size_t n, int word, int lvl, WideLayout &b) {
+    if (lvl < 2 || (size_t)word + 7 >= n) { b.ok = false; return wide_leaf(0, 0, b.ok); }
+    const size_t idx = b.wide.size() / 64;
+    if (idx >= 0x7FFFFFFFu) { b.ok = false; return wide_leaf(0, 0, b.ok); }
+    b.wide.resize(b.wide.size() + 64);
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++)
+            for (int k = 0; k < 4; k++) {
+                unsigned e;
+                int c1 = tree[(size_t)word + ((((i >> 1) & 1) << 2) | (((j >> 1) & 1) << 1) | ((k >> 1) & 1))];
+                if (c1 <= 0) {
+                    e = wide_leaf(c1, lvl - 1, b.ok);
+                } else if ((size_t)c1 + 7 >= n) {
+                    b.ok = false;
+                    e = wide_leaf(0, 0, b.ok);
+                } else {
+                    int c2 = tree[(size_t)c1 + (((i & 1) << 2) | ((j & 1) << 1) | (k & 1))];
+                    e = c2 <= 0 ? wide_leaf(c2, lvl - 2, b.ok) : wide_node(tree, n, c2, lvl - 2, b);
+                }
+                b.wide[idx * 64 + ((i << 4) | (j << 2) | k)] = e;
+            }
+    return (unsigned)idx;
+}
+
+WideLayout build_wide_layout(const int *tree, size_t n, int depth) {
+    WideLayout b;
+    int cl = std::max(depth - 7, 4);
+    if (cl & 1) cl++;
+    if (cl > depth) cl = depth & ~1;
+    b.cell_level = cl;
+    b.top_log2 = depth - cl;
+    const int dim = 1 << b.top_log2;
+    b.top.assign((size_t)dim * dim * dim, 0u);
+    for (int x = 0; x < dim && b.ok; x++)
+        for (int y = 0; y < dim; y++)
+            for (int z = 0; z < dim; z++) {
+                int level = depth;
+                int word = tree[0];
+                while (word > 0 && level > cl) {
+                    level--;
+                    int sh = level - cl;
+                    size_t at = (size_t)word + ((((x >> sh) & 1) << 2) | (((y >> sh) & 1) << 1) | ((z >> sh) & 1));
+                    if (at >= n) { b.ok = false; word = 0; break; }
+                    word = tree[at];
+                }
+                b.top[((size_t)x * dim + y) * dim + z] = word <= 0 ? wide_leaf(word, level, b.ok) : wide_node(tree, n, word, cl, b);
+            }
+    if (b.wide.empty()) b.wide.assign(64, wide_leaf(0, 0, b.ok));
+    return b;
+}
 }  // namespace
 
 extern "C" {
@@ -367,11 +451,17 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     c->device = device_index;
     c->sm_count = p.multiProcessorCount;
     if (const char *e = getenv("CCU_WAIT_LANES")) c->wait_lanes = std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("CCU_REFILL_MIN")) c->refill_min = std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("CCU_EXIT_IDLE")) c->exit_idle = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_BLOCKS_PER_SM")) c->blocks_per_sm = std::max(1, std::min(8, atoi(e)));
     DeviceGuard g(device_index);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaMalloc(&c->unorm, 256 * sizeof(float));
     if (e == cudaSuccess) {
         k_unorm_table<<<1, 256, 0, c->stream>>>(c->unorm);
@@ -394,7 +484,7 @@ int ccu_ctx_destroy(ccu_ctx *c) {
         std::lock_guard<std::mutex> lk(c->mu);
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
-        c->tree.release(); c->block_palette.release(); c->quad_models.release(); c->aabb_models.release();
+        c->tree.release(); c->top.release(); c->wide.release(); c->block_palette.release(); c->quad_models.release(); c->aabb_models.release();
         c->mat_palette.release(); c->trigs.release(); c->world_bvh.release(); c->actor_bvh.release();
         c->sun_words.release(); c->atlas.release(); c->sky.release(); c->rays.release(); c->sun_basis.release();
         if (c->accum) cudaFree(c->accum);
@@ -421,7 +511,10 @@ int ccu_scene_set_octree(ccu_ctx *c, const int32_t *tree, int64_t n, int32_t dep
     if (depth < 0 || depth > 30) return fail(CCU_EINVAL, "octree depth %d out of range", depth);
     if (n < 1) return fail(CCU_EINVAL, "octree needs at least the root word");
     int rc = upload_words(c, c->tree, tree, n, "ccu_scene_set_octree");
-    if (rc == CCU_OK) c->depth = depth;
+    if (rc == CCU_OK) {
+        c->depth = depth;
+        c->tree_host.assign(tree, tree + n);
+    }
     return rc;
 }
 int ccu_scene_set_block_palette(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->block_palette, w, n, "ccu_scene_set_block_palette"); }
@@ -528,6 +621,17 @@ int ccu_scene_commit(ccu_ctx *c) {
     if (!c->trigs.p) CU(c->trigs.upload(&zero, 0, c->stream));
     if (!c->world_bvh.p) { CU(c->world_bvh.upload(&zero, 0, c->stream)); c->world_head.clear(); }
     if (!c->actor_bvh.p) { CU(c->actor_bvh.upload(&zero, 0, c->stream)); c->actor_head.clear(); }
+    // traversal layout: dense top table + 64-ary nodes (two octree levels per load); falls back to the plain
+    // reference layout if a leaf value cannot be encoded
+    {
+        const bool enable = getenv("CCU_NO_WIDE") == nullptr;
+        WideLayout wl = build_wide_layout(c->tree_host.data(), c->tree_host.size(), c->depth);
+        c->use_wide = (enable && wl.ok) ? 1 : 0;
+        c->cell_level = wl.cell_level;
+        c->top_log2 = wl.top_log2;
+        CU(c->top.upload(wl.top.data(), wl.top.size(), c->stream));
+        CU(c->wide.upload(wl.wide.data(), wl.wide.size(), c->stream));
+    }
     // sun basis on the device
     if (!c->sun_basis.p) {
         float z[10] = {0};
@@ -644,13 +748,23 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
     if (!c->work_counter) CU(cudaMalloc(&c->work_counter, sizeof(unsigned int)));
     CU(cudaEventRecord(c->ev0, c->stream));
     if (c->params.kernel != 1) CU(cudaMemsetAsync(c->work_counter, 0, sizeof(unsigned int), c->stream));
+    const bool wide = c->scene.use_wide != 0;
+    const bool bvh = !(c->scene.world_bvh_empty && c->scene.actor_bvh_empty);
+#define CCU_DISPATCH(KERNEL, GRID, BLOCK, SMEM, ...)                                                              \
+    do {                                                                                                          \
+        if (bvh && wide) KERNEL<true, true><<<GRID, BLOCK, SMEM, c->stream>>>(__VA_ARGS__);                       \
+        else if (bvh) KERNEL<true, false><<<GRID, BLOCK, SMEM, c->stream>>>(__VA_ARGS__);                        \
+        else if (wide) KERNEL<false, true><<<GRID, BLOCK, SMEM, c->stream>>>(__VA_ARGS__);                       \
+        else KERNEL<false, false><<<GRID, BLOCK, SMEM, c->stream>>>(__VA_ARGS__);                                \
+    } while (0)
     if (c->params.kernel == 1) {
         int threads = 128;
         int blocks = (n_pixels + threads - 1) / threads;
-        k_render_mega<<<blocks, threads, 0, c->stream>>>(c->scene, c->seeds_dev, n_passes, c->window_spp, c->accum, n_pixels);
+        if (wide) k_render_mega<true><<<blocks, threads, 0, c->stream>>>(c->scene, c->seeds_dev, n_passes, c->window_spp, c->accum, n_pixels);
+        else k_render_mega<false><<<blocks, threads, 0, c->stream>>>(c->scene, c->seeds_dev, n_passes, c->window_spp, c->accum, n_pixels);
         c->launches++;
     } else {
-        // persistent wavefront kernel: one resident grid, pixels handed out through a counter
+        // persistent kernels: one resident grid, pixels handed out through a counter
         WaveParams wp;
         wp.seeds = c->seeds_dev;
         wp.n_passes = n_passes;
@@ -660,12 +774,20 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
         wp.next_pixel = c->work_counter;
         wp.wait_lanes = c->wait_lanes;
         int blocks = c->sm_count * c->blocks_per_sm;
-        if (c->scene.world_bvh_empty && c->scene.actor_bvh_empty)
-            k_render_wave<false><<<blocks, 256, 0, c->stream>>>(c->scene, wp);
-        else
-            k_render_wave<true><<<blocks, 256, 0, c->stream>>>(c->scene, wp);
+        if (c->params.kernel == 3) {
+            // lane-bound state machine (ccu_wavefront.cuh)
+            CCU_DISPATCH(k_render_wave, blocks, 256, 0, c->scene, wp);
+        } else {
+            // per-warp path pool in shared memory (ccu_pool.cuh)
+            PoolParams pp;
+            pp.w = wp;
+            pp.refill_min = c->refill_min;
+            pp.exit_idle = c->exit_idle;
+            CCU_DISPATCH(k_render_pool, blocks, POOL_WARPS * 32, POOL_SMEM_BYTES, c->scene, pp);
+        }
         c->launches++;
     }
+#undef CCU_DISPATCH
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev1, c->stream));
     c->timing_pending = true;
@@ -855,7 +977,7 @@ int ccu_launch_count(ccu_ctx *c, int64_t *launches) {
 int ccu_scene_device_bytes(ccu_ctx *c, int64_t *bytes) {
     if (!c || !bytes) return fail(CCU_EINVAL, "ccu_scene_device_bytes: null argument");
     std::lock_guard<std::mutex> lk(c->mu);
-    *bytes = (int64_t)(c->tree.bytes() + c->block_palette.bytes() + c->quad_models.bytes() + c->aabb_models.bytes() + c->mat_palette.bytes() +
+    *bytes = (int64_t)(c->tree.bytes() + c->top.bytes() + c->wide.bytes() + c->block_palette.bytes() + c->quad_models.bytes() + c->aabb_models.bytes() + c->mat_palette.bytes() +
                        c->trigs.bytes() + c->world_bvh.bytes() + c->actor_bvh.bytes() + c->atlas.bytes() + c->sky.bytes());
     return CCU_OK;
 }

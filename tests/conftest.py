@@ -22,6 +22,10 @@ def scenes():
         if name not in cache:
             if name == "terrain64":
                 cache[name] = S.terrain_scene(64, 160, 90, seed=7)
+            elif name == "tiny8":
+                cache[name] = S.terrain_scene(8, 64, 36, seed=3)            # depth 3: top table only two cells wide
+            elif name == "terrain128":
+                cache[name] = S.terrain_scene(128, 160, 90, seed=5)         # odd depth (7)
             elif name == "terrain256":
                 cache[name] = S.terrain_scene(256, 320, 180)
             elif name == "terrain256_nosun":

@@ -11,7 +11,7 @@ from conftest import load_scene
 
 pytestmark = pytest.mark.gpu
 
-ALL = ["terrain64", "terrain256", "terrain256_nosun", "decorated", "mixed", "indoor", "entities"]
+ALL = ["tiny8", "terrain64", "terrain128", "terrain256", "terrain256_nosun", "decorated", "mixed", "indoor", "entities"]
 
 
 def _bits(a):
@@ -33,7 +33,7 @@ def test_first_hit_bit_exact(name, scenes, cuda_ctx):
     assert (ref["kind"] > 0).any()
 
 
-@pytest.mark.parametrize("kernel", [2, 1], ids=["wavefront", "megakernel"])
+@pytest.mark.parametrize("kernel", [2, 3, 1], ids=["pool", "wavefront", "megakernel"])
 @pytest.mark.parametrize("name", ALL)
 def test_render_bit_exact(name, kernel, scenes, cuda_ctx):
     """Both render kernels (persistent wavefront = default, thread-per-pixel megakernel) against the oracle."""
@@ -158,3 +158,25 @@ def test_errors_are_loud(cuda_ctx):
         c.close()
     with pytest.raises(native.ChunkyCuError):
         native.Context(999)
+
+
+def test_reference_layout_descent_equals_wide_layout(scenes):
+    """CCU_NO_WIDE=1 keeps the reference's root-descent layout on the device; images must not change."""
+    import os
+    from chunkyclplugin_b200 import native
+    p = scenes("decorated")
+    seeds = pass_seeds(3)
+    imgs = []
+    for flag in ("1", None):
+        if flag:
+            os.environ["CCU_NO_WIDE"] = flag
+        else:
+            os.environ.pop("CCU_NO_WIDE", None)
+        c = native.Context(0)
+        try:
+            load_scene(c, p)
+            c.render_passes(seeds)
+            imgs.append(c.render_read()[0])
+        finally:
+            c.close()
+    assert np.array_equal(_bits(imgs[0]), _bits(imgs[1]))
