@@ -52,7 +52,7 @@ struct PoolParams {
 };
 
 template <bool HAS_BVH, bool WIDE>
-__global__ void __launch_bounds__(POOL_WARPS * 32, 2) k_render_pool(const __grid_constant__ DScene s, const __grid_constant__ PoolParams pp) {
+__global__ void __launch_bounds__(POOL_WARPS * 32, CCU_MIN_BLOCKS) k_render_pool(const __grid_constant__ DScene s, const __grid_constant__ PoolParams pp) {
     extern __shared__ uint32_t pool_mem[];
     const WaveParams &w = pp.w;
     const unsigned full = 0xffffffffu;

@@ -11,6 +11,10 @@
 #pragma once
 #include "ccu_device.cuh"
 
+#ifndef CCU_MIN_BLOCKS
+#define CCU_MIN_BLOCKS 3
+#endif
+
 namespace ccu {
 
 enum LaneState : int {
@@ -35,7 +39,7 @@ struct WaveParams {
 };
 
 template <bool HAS_BVH, bool WIDE>
-__global__ void __launch_bounds__(256, 2) k_render_wave(const __grid_constant__ DScene s, const __grid_constant__ WaveParams w) {
+__global__ void __launch_bounds__(256, CCU_MIN_BLOCKS) k_render_wave(const __grid_constant__ DScene s, const __grid_constant__ WaveParams w) {
     const unsigned full = 0xffffffffu;
     // pixel / pass
     int gid = -1, pass = 0;

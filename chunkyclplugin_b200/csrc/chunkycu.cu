@@ -228,10 +228,10 @@ struct ccu_ctx {
     float *pinned = nullptr;     // host staging float[3*W*H]
     int *seeds_dev = nullptr;
     unsigned int *work_counter = nullptr;
-    int wait_lanes = 24;
+    int wait_lanes = 28;
     int refill_min = 4;
     int exit_idle = 8;
-    int blocks_per_sm = 2;
+    int blocks_per_sm = CCU_MIN_BLOCKS;
     int seeds_cap = 0;
     int window_spp = 0;
     bool target_live = false;    // between ccu_render_begin and ccu_render_end
@@ -774,8 +774,8 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
         wp.next_pixel = c->work_counter;
         wp.wait_lanes = c->wait_lanes;
         int blocks = c->sm_count * c->blocks_per_sm;
-        if (c->params.kernel == 3) {
-            // lane-bound state machine (ccu_wavefront.cuh)
+        if (c->params.kernel == 3 || c->params.kernel == 0) {
+            // lane-bound state machine (ccu_wavefront.cuh) - currently the fastest, hence the default
             CCU_DISPATCH(k_render_wave, blocks, 256, 0, c->scene, wp);
         } else {
             // per-warp path pool in shared memory (ccu_pool.cuh)

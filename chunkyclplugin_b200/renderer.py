@@ -213,10 +213,17 @@ class CudaPathTracingRenderer:
             rand = JavaRandom(0)                             # :95
             self.kernel_ms = 0.0
             while logicalSpp < scene.getTargetSpp():         # :102
-                remaining_to_target = scene.getTargetSpp() - (logicalSpp + bufferSppReal)
-                n = min(self.MERGE_WINDOW - bufferSppReal, max(remaining_to_target, 1))
+                # The reference issues one pass per launch and tests for a save event after each (:150).  Here one
+                # C-ABI call covers all passes up to the next point where the reference would merge: the next save
+                # event (snapshot / dump / target spp) or a full window - found by probing the same predicate.
+                n = self.MERGE_WINDOW - bufferSppReal
                 if self.passes_per_call > 0:
                     n = min(n, self.passes_per_call)
+                control = manager.getSnapshotControl()
+                for k in range(1, n + 1):
+                    if self._isSaveEvent(control, scene, logicalSpp + bufferSppReal + k):
+                        n = k
+                        break
                 seeds = np.array([rand.next_int() for _ in range(n)], dtype=np.int32)      # :106-107
                 with renderLock:
                     ctx.render_passes(seeds)                 # :108-141 (bufferSpp tracked by the library)

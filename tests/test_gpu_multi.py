@@ -1,0 +1,60 @@
+"""Sample-parallel rendering across 2 GPUs (NCCL): N-GPU image == 1-GPU image up to fp32 summation order."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_passes, out_path):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from chunkyclplugin_b200 import native, scenes as S
+        from chunkyclplugin_b200.javarandom import pass_seeds
+        from chunkyclplugin_b200.multigpu import SampleParallelRenderer
+        from conftest import load_scene
+        p = S.terrain_scene(64, 160, 90, seed=7)
+        ctx = native.Context(rank)
+        load_scene(ctx, p)
+        spr = SampleParallelRenderer(ctx, rank, world)
+        n_local = spr.render_window(pass_seeds(n_passes))
+        out, n = spr.reduce_window(n_local)
+        if rank == 0:
+            assert n == n_passes
+            np.save(out_path, out.cpu().numpy())
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_reduce_matches_one_gpu(tmp_path, scenes, cuda_ctx):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from chunkyclplugin_b200.javarandom import pass_seeds
+    from conftest import load_scene
+    n_passes = 7
+    out_path = str(tmp_path / "combined.npy")
+    mp.spawn(_worker, args=(2, _free_port(), n_passes, out_path), nprocs=2, join=True)
+    combined = np.load(out_path)
+    p = scenes("terrain64")
+    load_scene(cuda_ctx, p)
+    cuda_ctx.render_passes(pass_seeds(n_passes))
+    one, _ = cuda_ctx.render_read()
+    assert np.allclose(combined, one, rtol=2e-6, atol=1e-7)
