@@ -94,10 +94,11 @@ def cpu_port_rate(scene, seeds, stride: int, threads: int = 0):
     o = oracle.Oracle(scene)
     gids = np.arange(0, scene.width * scene.height, stride, dtype=np.int32)
     t0 = time.perf_counter()
+    threads = threads or (os.cpu_count() or 1)          # torchrun exports OMP_NUM_THREADS=1; use every host core anyway
     o.render(seeds, gids=gids, threads=threads)
     dt = time.perf_counter() - t0
     n = gids.size * len(seeds)
-    return n / dt, o.last_counters, n, (threads or oracle.num_threads())
+    return n / dt, o.last_counters, n, threads
 
 
 def run_reference(args):
