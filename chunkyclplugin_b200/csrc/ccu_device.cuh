@@ -22,6 +22,10 @@ struct DScene {
     const unsigned *__restrict__ wide;
     int cell_level, top_log2;
     int use_wide;
+    // march-loop ("air") layout: same table / node shape, entries carry only air-or-not + level, finest nodes are 128-bit maps
+    const unsigned *__restrict__ air_top;
+    const unsigned *__restrict__ air_wide;
+    const unsigned *__restrict__ air_bits;
     // palettes (reference packed layouts)
     const int *__restrict__ block_palette;
     int block_palette_len;

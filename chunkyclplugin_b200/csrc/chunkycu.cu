@@ -16,6 +16,7 @@
 #include "ccu_device.cuh"
 #include "ccu_wavefront.cuh"
 #include "ccu_pool.cuh"
+#include "ccu_queue.cuh"
 
 using namespace ccu;
 
@@ -206,6 +207,8 @@ struct ccu_ctx {
     DevBuf<uchar4> atlas, sky;
     std::vector<int> tree_host;              // kept for the commit-time traversal layout
     DevBuf<unsigned> top, wide;
+    DevBuf<unsigned> air_top, air_wide, air_bits;   // march-loop layout (ccu_queue.cuh)
+    int use_air = 0;
     int cell_level = 0, top_log2 = 0, use_wide = 0;
     int atlas_w = 0, atlas_h = 0, atlas_layers = 0;
     int depth = 0, sky_res = 0;
@@ -231,6 +234,8 @@ struct ccu_ctx {
     int wait_lanes = 28;
     int refill_min = 4;
     int exit_idle = 8;
+    int yield_below = 16;
+    int q_refill_min = 8;
     int blocks_per_sm = CCU_MIN_BLOCKS;
     int seeds_cap = 0;
     int window_spp = 0;
@@ -278,6 +283,9 @@ int fill_scene(ccu_ctx *c) {
     s.cell_level = c->cell_level;
     s.top_log2 = c->top_log2;
     s.use_wide = c->use_wide;
+    s.air_top = c->air_top.p;
+    s.air_wide = c->air_wide.p;
+    s.air_bits = c->air_bits.p;
     s.block_palette = c->block_palette.p;
     s.block_palette_len = (int)c->block_palette.n;
     s.quad_models = c->quad_models.p;
@@ -373,6 +381,91 @@ unsigned wide_node(const int *tree, size_t n, int word, int lvl, WideLayout &b) 
     return (unsigned)idx;
 }
 
+// "Air layout" for the march loop (ccu_queue.cuh lean_probe): the same top table / 64-ary nodes, but an entry only says
+// air or not (bit 0 = 1: not air) plus the leaf level, and the finest nodes (4^3 voxels) shrink from 64 words to a
+// 128-bit map of 2-bit codes (0 = not air, 1 = air leaf of level 0, 2 = air leaf of level 1).  The march loop needs
+// nothing else (octree.h:89-106: an air leaf is left through its cube, anything else goes to the block test), and the
+// structure is ~10x smaller than the value-carrying layout, which is what keeps it in L1.
+struct AirLayout {
+    std::vector<unsigned> top, wide, bits;
+    bool ok = true;
+};
+
+inline unsigned air_leaf(int word, int level) { return CCU_WIDE_LEAF | ((unsigned)level << 26) | (word == 0 ? 0u : 1u); }
+
+unsigned air_node(const int *tree, size_t n, int word, int lvl, AirLayout &b) {
+    if (lvl < 2 || (size_t)word + 7 >= n) { b.ok = false; return air_leaf(1, 0); }
+    if (lvl == 2) {
+        const size_t idx = b.bits.size() / 4;
+        if (idx >= 0x7FFFFFFFu) { b.ok = false; return air_leaf(1, 0); }
+        b.bits.resize(b.bits.size() + 4, 0u);
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++)
+                for (int k = 0; k < 4; k++) {
+                    unsigned code;
+                    int c1 = tree[(size_t)word + ((((i >> 1) & 1) << 2) | (((j >> 1) & 1) << 1) | ((k >> 1) & 1))];
+                    if (c1 <= 0) {
+                        code = c1 == 0 ? 2u : 0u;
+                    } else if ((size_t)c1 + 7 >= n) {
+                        b.ok = false;
+                        code = 0;
+                    } else {
+                        int c2 = tree[(size_t)c1 + (((i & 1) << 2) | ((j & 1) << 1) | (k & 1))];
+                        if (c2 > 0) b.ok = false;          // deeper than the declared depth
+                        code = c2 == 0 ? 1u : 0u;
+                    }
+                    const int v = (i << 4) | (j << 2) | k;
+                    b.bits[idx * 4 + (v >> 4)] |= code << ((v & 15) * 2);
+                }
+        return (unsigned)idx;
+    }
+    const size_t idx = b.wide.size() / 64;
+    if (idx >= 0x7FFFFFFFu) { b.ok = false; return air_leaf(1, 0); }
+    b.wide.resize(b.wide.size() + 64);
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++)
+            for (int k = 0; k < 4; k++) {
+                unsigned e;
+                int c1 = tree[(size_t)word + ((((i >> 1) & 1) << 2) | (((j >> 1) & 1) << 1) | ((k >> 1) & 1))];
+                if (c1 <= 0) {
+                    e = air_leaf(c1, lvl - 1);
+                } else if ((size_t)c1 + 7 >= n) {
+                    b.ok = false;
+                    e = air_leaf(1, 0);
+                } else {
+                    int c2 = tree[(size_t)c1 + (((i & 1) << 2) | ((j & 1) << 1) | (k & 1))];
+                    e = c2 <= 0 ? air_leaf(c2, lvl - 2) : air_node(tree, n, c2, lvl - 2, b);
+                }
+                b.wide[idx * 64 + ((i << 4) | (j << 2) | k)] = e;
+            }
+    return (unsigned)idx;
+}
+
+// same cell level / table shape as the wide layout
+AirLayout build_air_layout(const int *tree, size_t n, int depth, int cl) {
+    AirLayout b;
+    const int dim = 1 << (depth - cl);
+    b.top.assign((size_t)dim * dim * dim, 0u);
+    for (int x = 0; x < dim && b.ok; x++)
+        for (int y = 0; y < dim; y++)
+            for (int z = 0; z < dim; z++) {
+                int level = depth;
+                int word = tree[0];
+                while (word > 0 && level > cl) {
+                    level--;
+                    int sh = level - cl;
+                    size_t at = (size_t)word + ((((x >> sh) & 1) << 2) | (((y >> sh) & 1) << 1) | ((z >> sh) & 1));
+                    if (at >= n) { b.ok = false; word = 0; break; }
+                    word = tree[at];
+                }
+                if (word > 0 && cl < 2) { b.ok = false; word = -1; }
+                b.top[((size_t)x * dim + y) * dim + z] = word <= 0 ? air_leaf(word, level) : air_node(tree, n, word, cl, b);
+            }
+    if (b.wide.empty()) b.wide.assign(64, air_leaf(1, 0));
+    if (b.bits.empty()) b.bits.assign(4, 0u);
+    return b;
+}
+
 WideLayout build_wide_layout(const int *tree, size_t n, int depth) {
     WideLayout b;
     int cl = std::max(depth - 7, 4);
@@ -453,6 +546,8 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     if (const char *e = getenv("CCU_WAIT_LANES")) c->wait_lanes = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_REFILL_MIN")) c->refill_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_EXIT_IDLE")) c->exit_idle = std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("CCU_Q_REFILL_MIN")) c->q_refill_min = std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("CCU_YIELD_BELOW")) c->yield_below = std::max(0, std::min(33, atoi(e)));
     if (const char *e = getenv("CCU_BLOCKS_PER_SM")) c->blocks_per_sm = std::max(1, std::min(8, atoi(e)));
     DeviceGuard g(device_index);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -462,6 +557,10 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES_TOP);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES_TOP);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaMalloc(&c->unorm, 256 * sizeof(float));
     if (e == cudaSuccess) {
         k_unorm_table<<<1, 256, 0, c->stream>>>(c->unorm);
@@ -484,7 +583,7 @@ int ccu_ctx_destroy(ccu_ctx *c) {
         std::lock_guard<std::mutex> lk(c->mu);
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
-        c->tree.release(); c->top.release(); c->wide.release(); c->block_palette.release(); c->quad_models.release(); c->aabb_models.release();
+        c->tree.release(); c->top.release(); c->wide.release(); c->air_top.release(); c->air_wide.release(); c->air_bits.release(); c->block_palette.release(); c->quad_models.release(); c->aabb_models.release();
         c->mat_palette.release(); c->trigs.release(); c->world_bvh.release(); c->actor_bvh.release();
         c->sun_words.release(); c->atlas.release(); c->sky.release(); c->rays.release(); c->sun_basis.release();
         if (c->accum) cudaFree(c->accum);
@@ -631,6 +730,11 @@ int ccu_scene_commit(ccu_ctx *c) {
         c->top_log2 = wl.top_log2;
         CU(c->top.upload(wl.top.data(), wl.top.size(), c->stream));
         CU(c->wide.upload(wl.wide.data(), wl.wide.size(), c->stream));
+        AirLayout al = build_air_layout(c->tree_host.data(), c->tree_host.size(), c->depth, wl.cell_level);
+        c->use_air = al.ok ? 1 : 0;
+        CU(c->air_top.upload(al.top.data(), al.top.size(), c->stream));
+        CU(c->air_wide.upload(al.wide.data(), al.wide.size(), c->stream));
+        CU(c->air_bits.upload(al.bits.data(), al.bits.size(), c->stream));
     }
     // sun basis on the device
     if (!c->sun_basis.p) {
@@ -708,7 +812,7 @@ int ccu_render_begin(ccu_ctx *c, int32_t width, int32_t height) {
 
 int ccu_render_set_params(ccu_ctx *c, const ccu_render_params *p) {
     if (!c || !p) return fail(CCU_EINVAL, "ccu_render_set_params: null argument");
-    if (p->draw_depth < 0 || p->max_depth < 1) return fail(CCU_EINVAL, "bad render params");
+    if (p->draw_depth < 0 || p->draw_depth >= (1 << 24) || p->max_depth < 1 || p->max_depth > 255) return fail(CCU_EINVAL, "bad render params");
     std::lock_guard<std::mutex> lk(c->mu);
     c->params = *p;
     return CCU_OK;
@@ -774,8 +878,38 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
         wp.next_pixel = c->work_counter;
         wp.wait_lanes = c->wait_lanes;
         int blocks = c->sm_count * c->blocks_per_sm;
-        if (c->params.kernel == 3 || c->params.kernel == 0) {
-            // lane-bound state machine (ccu_wavefront.cuh) - currently the fastest, hence the default
+        if (c->params.kernel == 4 || c->params.kernel == 0) {
+            // CTA-wide path pool with per-stage work masks (ccu_queue.cuh): one CTA per SM - the fastest, hence the default
+            QueueParams qp;
+            qp.w = wp;
+            qp.yield_below = c->yield_below;
+            qp.refill_min = c->q_refill_min;
+            const bool tops = c->air_top.n <= (size_t)Q_TOP_WORDS && getenv("CCU_NO_TOPS") == nullptr;
+            const int grid = c->sm_count, block = Q_WARPS * 32;
+            if (!c->use_air) return fail(CCU_ESTATE, "ccu_render_passes: kernel 4 needs the air layout (malformed octree?)");
+            if (tops) {
+                if (bvh) k_render_queue<true, true><<<grid, block, Q_SMEM_BYTES_TOP, c->stream>>>(c->scene, qp);
+                else k_render_queue<false, true><<<grid, block, Q_SMEM_BYTES_TOP, c->stream>>>(c->scene, qp);
+            } else {
+                if (bvh) k_render_queue<true, false><<<grid, block, Q_SMEM_BYTES, c->stream>>>(c->scene, qp);
+                else k_render_queue<false, false><<<grid, block, Q_SMEM_BYTES, c->stream>>>(c->scene, qp);
+            }
+#ifdef CCU_Q_STATS
+            {
+                cudaStreamSynchronize(c->stream);
+                unsigned long long st[16];
+                cudaMemcpyFromSymbol(st, g_qstats, sizeof st);
+                const char *names[5] = {"march", "block", "exit", "bounce", "end"};
+                fprintf(stderr, "[qstats] ");
+                for (int i = 1; i < 5; i++) fprintf(stderr, "%s: %llu x %.1f lanes  ", names[i], st[2 * i], st[2 * i] ? (double)st[2 * i + 1] / st[2 * i] : 0.0);
+                fprintf(stderr, "\n[qstats] march stages %llu, iterations %llu x %.1f lanes in flight, yields %llu, idle rounds %llu, pops %llu retries %llu\n", st[0], st[10],
+                        st[10] ? (double)st[11] / st[10] : 0.0, st[13], st[12], st[14], st[15]);
+                unsigned long long z[16] = {0};
+                cudaMemcpyToSymbol(g_qstats, z, sizeof z);
+            }
+#endif
+        } else if (c->params.kernel == 3) {
+            // lane-bound state machine (ccu_wavefront.cuh)
             CCU_DISPATCH(k_render_wave, blocks, 256, 0, c->scene, wp);
         } else {
             // per-warp path pool in shared memory (ccu_pool.cuh)
@@ -977,7 +1111,7 @@ int ccu_launch_count(ccu_ctx *c, int64_t *launches) {
 int ccu_scene_device_bytes(ccu_ctx *c, int64_t *bytes) {
     if (!c || !bytes) return fail(CCU_EINVAL, "ccu_scene_device_bytes: null argument");
     std::lock_guard<std::mutex> lk(c->mu);
-    *bytes = (int64_t)(c->tree.bytes() + c->top.bytes() + c->wide.bytes() + c->block_palette.bytes() + c->quad_models.bytes() + c->aabb_models.bytes() + c->mat_palette.bytes() +
+    *bytes = (int64_t)(c->tree.bytes() + c->top.bytes() + c->wide.bytes() + c->air_top.bytes() + c->air_wide.bytes() + c->air_bits.bytes() + c->block_palette.bytes() + c->quad_models.bytes() + c->aabb_models.bytes() + c->mat_palette.bytes() +
                        c->trigs.bytes() + c->world_bvh.bytes() + c->actor_bvh.bytes() + c->atlas.bytes() + c->sky.bytes());
     return CCU_OK;
 }

@@ -42,7 +42,7 @@ typedef struct ccu_render_params {
     int32_t draw_depth;    /* octree march step limit */
     int32_t max_depth;     /* ray depth limit (5 = 4 bounces) */
     float emitter_scale;   /* emitter intensity factor */
-    int32_t kernel;        /* 0 = auto (currently 3), 1 = thread-per-pixel megakernel, 2 = persistent wavefront with per-warp path pool in shared memory, 3 = persistent wavefront with lane-bound paths */
+    int32_t kernel;        /* 0 = auto (currently 4), 1 = thread-per-pixel megakernel, 2 = persistent wavefront with per-warp path pool in shared memory, 3 = persistent wavefront with lane-bound paths, 4 = persistent wavefront with a CTA-wide path pool and per-stage work masks */
 } ccu_render_params;
 
 /* ---- device enumeration: RendererInstance.java:39-75,123-157 (clGetPlatformIDs/clGetDeviceIDs/clGetDeviceInfo),
