@@ -76,7 +76,8 @@ __device__ unsigned long long g_qstats[16];
 struct QueueParams {
     WaveParams w;
     int yield_below;   // MARCH: consider switching stage once fewer lanes than this are busy
-    int refill_min;    // MARCH: refill idle lanes once this many lanes are idle
+    int refill_min;    // MARCH: hand over / refill once this many lanes hold a finished ray
+    int march_bias;    // scheduler: warps of sub-partitions 0..2 count MARCH columns +bias, warps of sub-partition 3 -bias
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -505,7 +506,10 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
         int best = -1, best_n = 0;
 #pragma unroll
         for (int st = 0; st < QS_COUNT; st++) {
-            const int n = __popc(__ballot_sync(full, q_has_work(mask, st, lane)));
+            int n = __popc(__ballot_sync(full, q_has_work(mask, st, lane)));
+            // Warps of one SM sub-partition share an instruction cache: three sub-partitions lean towards the (small)
+            // march loop, the fourth towards the (large) shading stages.
+            if (st == QS_MARCH && n > 0) n = max(1, n + ((threadIdx.x >> 5 & 3) == 3 ? -qp.march_bias : qp.march_bias));
             if (n > best_n) { best_n = n; best = st; }
         }
         if (best < 0) {

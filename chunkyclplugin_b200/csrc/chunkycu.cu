@@ -148,6 +148,40 @@ __global__ void k_atlas_write(uchar4 *atlas, int tiles_x, int tiles_y, int x0, i
     atlas[tile * 256 + ((y & 15) << 4) + (x & 15)] = src[i];
 }
 
+// Roofline denominators this path needs: random 32-byte-sector gathers.  Every thread issues `loads`
+// independent 16-byte L2 loads (ld.global.cg) at hashed sector addresses of an array of `sectors` sectors
+// (dependent = 0), or walks a dependent chain (dependent = 1: the next address comes from the loaded word).
+__global__ void k_gather_fill(uint4 *a, size_t sectors, uint32_t seed) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < sectors * 2; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + seed;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        a[i] = make_uint4(h, h * 3u + 1u, h ^ 0x9e3779b9u, (uint32_t)i);
+    }
+}
+__global__ void __launch_bounds__(256) k_gather(const uint4 *__restrict__ a, uint32_t sector_mask, int loads, int dependent, uint32_t *sink) {
+    uint32_t st = (blockIdx.x * blockDim.x + threadIdx.x) * 747796405u + 2891336453u;
+    uint32_t acc = 0;
+    if (dependent) {
+        // one thread per SM walks the chain: the time per load is the latency of one dependent gather
+        if (threadIdx.x != 0) return;
+        uint32_t at = st & sector_mask;
+        for (int i = 0; i < loads; i++) {
+            uint4 v = __ldcg(a + (size_t)at * 2);
+            acc ^= v.y;
+            at = (v.x ^ (uint32_t)i * 0x9e3779b9u) & sector_mask;
+        }
+    } else {
+#pragma unroll 8
+        for (int i = 0; i < loads; i++) {
+            st = st * 747796405u + 2891336453u;
+            uint32_t at = ((st >> 9) ^ st) & sector_mask;
+            uint4 v = __ldcg(a + (size_t)at * 2);
+            acc ^= v.x ^ v.w;
+        }
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+
 // ======================================================================================================
 // host side
 // ======================================================================================================
@@ -236,6 +270,7 @@ struct ccu_ctx {
     int exit_idle = 8;
     int yield_below = 16;
     int q_refill_min = 8;
+    int q_march_bias = 4;
     int blocks_per_sm = CCU_MIN_BLOCKS;
     int seeds_cap = 0;
     int window_spp = 0;
@@ -546,6 +581,7 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     if (const char *e = getenv("CCU_WAIT_LANES")) c->wait_lanes = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_REFILL_MIN")) c->refill_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_EXIT_IDLE")) c->exit_idle = std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("CCU_Q_MARCH_BIAS")) c->q_march_bias = std::max(-32, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_Q_REFILL_MIN")) c->q_refill_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_YIELD_BELOW")) c->yield_below = std::max(0, std::min(33, atoi(e)));
     if (const char *e = getenv("CCU_BLOCKS_PER_SM")) c->blocks_per_sm = std::max(1, std::min(8, atoi(e)));
@@ -884,6 +920,7 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
             qp.w = wp;
             qp.yield_below = c->yield_below;
             qp.refill_min = c->q_refill_min;
+            qp.march_bias = c->q_march_bias;
             const bool tops = c->air_top.n <= (size_t)Q_TOP_WORDS && getenv("CCU_NO_TOPS") == nullptr;
             const int grid = c->sm_count, block = Q_WARPS * 32;
             if (!c->use_air) return fail(CCU_ESTATE, "ccu_render_passes: kernel 4 needs the air layout (malformed octree?)");
@@ -1113,6 +1150,87 @@ int ccu_scene_device_bytes(ccu_ctx *c, int64_t *bytes) {
     std::lock_guard<std::mutex> lk(c->mu);
     *bytes = (int64_t)(c->tree.bytes() + c->top.bytes() + c->wide.bytes() + c->air_top.bytes() + c->air_wide.bytes() + c->air_bits.bytes() + c->block_palette.bytes() + c->quad_models.bytes() + c->aabb_models.bytes() + c->mat_palette.bytes() +
                        c->trigs.bytes() + c->world_bvh.bytes() + c->actor_bvh.bytes() + c->atlas.bytes() + c->sky.bytes());
+    return CCU_OK;
+}
+
+int ccu_bench_gather(ccu_ctx *c, int64_t array_bytes, int32_t dependent, float *gbytes_per_s, float *ns_per_load) {
+    if (!c || array_bytes < 4096) return fail(CCU_EINVAL, "ccu_bench_gather: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    size_t sectors = 1;
+    while (sectors * 2 * 32 <= (size_t)array_bytes) sectors *= 2;   // power of two number of 32-byte sectors
+    uint4 *a = nullptr;
+    uint32_t *sink = nullptr;
+    CU(cudaMalloc(&a, sectors * 32));
+    cudaError_t e = cudaMalloc(&sink, 4);
+    if (e != cudaSuccess) { cudaFree(a); return fail(CCU_ENOMEM, "ccu_bench_gather: %s", cudaGetErrorString(e)); }
+    k_gather_fill<<<c->sm_count * 8, 256, 0, c->stream>>>(a, sectors, 12345u);
+    const int loads = dependent ? 2048 : 4096;
+    const int blocks = dependent ? c->sm_count : c->sm_count * 8;
+    float best = 1e30f;
+    for (int it = 0; it < 4; it++) {   // first iteration warms the caches
+        cudaEventRecord(c->ev0, c->stream);
+        k_gather<<<blocks, dependent ? 32 : 256, 0, c->stream>>>(a, (uint32_t)(sectors - 1), loads, dependent, sink);
+        cudaEventRecord(c->ev1, c->stream);
+        e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        if (it > 0) best = std::min(best, ms);
+    }
+    c->launches += 5;
+    cudaFree(a);
+    cudaFree(sink);
+    if (e != cudaSuccess) return fail(CCU_ECUDA, "ccu_bench_gather: %s", cudaGetErrorString(e));
+    const double n_loads = (double)blocks * (dependent ? 1.0 : 256.0) * loads;
+    if (gbytes_per_s) *gbytes_per_s = (float)(n_loads * 32.0 / (best * 1e-3) / 1e9);
+    if (ns_per_load) *ns_per_load = (float)(best * 1e6 / loads);   // per thread: meaningful for the dependent chain
+    return CCU_OK;
+}
+
+// Host-only check of the commit-time traversal layouts (no CUDA call): for every voxel of `xyz` (count x 3 ints) returns what
+// the value-carrying layout (find_leaf_wide) and the air layout (lean_probe) answer, so that CPU tests can compare both
+// with the reference's root descent (octree.h:81-88).
+int ccu_debug_layout_lookup(const int32_t *tree, int64_t n, int32_t depth, const int32_t *xyz, int64_t count, int32_t *wide_value,
+                            int32_t *wide_level, int32_t *air_solid, int32_t *air_level) {
+    if (!tree || n < 1 || depth < 0 || depth > 30 || (count > 0 && !xyz)) return fail(CCU_EINVAL, "ccu_debug_layout_lookup: bad argument");
+    WideLayout wl = build_wide_layout(tree, (size_t)n, depth);
+    AirLayout al = build_air_layout(tree, (size_t)n, depth, wl.cell_level);
+    if (!al.ok) return fail(CCU_ESTATE, "air layout could not be built");
+    const int cl = wl.cell_level, tl = wl.top_log2;
+    for (int64_t i = 0; i < count; i++) {
+        const int bx = xyz[3 * i], by = xyz[3 * i + 1], bz = xyz[3 * i + 2];
+        if (((bx | by | bz) >> depth) != 0) return fail(CCU_EINVAL, "voxel %lld outside the octree cube", (long long)i);
+        const size_t cell = ((((size_t)(bx >> cl) << tl) + (size_t)(by >> cl)) << tl) + (size_t)(bz >> cl);
+        if (wl.ok) {
+            unsigned e = wl.top[cell];
+            int lvl = cl;
+            while (!(e & CCU_WIDE_LEAF)) {
+                lvl -= 2;
+                e = wl.wide[(size_t)e * 64 + ((((bx >> lvl) & 3) << 4) | (((by >> lvl) & 3) << 2) | ((bz >> lvl) & 3))];
+            }
+            const unsigned v = e & CCU_WIDE_ANY;
+            if (wide_value) wide_value[i] = v == CCU_WIDE_ANY ? CCU_ANY_TYPE : (int)v;
+            if (wide_level) wide_level[i] = (int)((e >> 26) & 31);
+        } else {
+            if (wide_value) wide_value[i] = -1;
+            if (wide_level) wide_level[i] = -1;
+        }
+        unsigned e = al.top[cell];
+        int lvl = cl;
+        while (!(e & CCU_WIDE_LEAF)) {
+            if (lvl == 2) {
+                const unsigned v = (unsigned)(((bx & 3) << 4) | ((by & 3) << 2) | (bz & 3));
+                const unsigned code = (al.bits[(size_t)e * 4 + (v >> 4)] >> ((v & 15u) * 2u)) & 3u;
+                e = CCU_WIDE_LEAF | (code == 0 ? 1u : ((code - 1u) << 26));
+                break;
+            }
+            lvl -= 2;
+            e = al.wide[(size_t)e * 64 + ((((bx >> lvl) & 3) << 4) | (((by >> lvl) & 3) << 2) | ((bz >> lvl) & 3))];
+        }
+        if (air_solid) air_solid[i] = (int)(e & 1u);
+        if (air_level) air_level[i] = (e & 1u) ? -1 : (int)((e >> 26) & 31);
+    }
     return CCU_OK;
 }
 

@@ -71,6 +71,8 @@ SYMBOLS = {
     "ccu_last_kernel_ms": (C.c_int, [_vp, C.POINTER(_f)]),
     "ccu_launch_count": (C.c_int, [_vp, C.POINTER(_i64)]),
     "ccu_scene_device_bytes": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "ccu_bench_gather": (C.c_int, [_vp, _i64, _i32, C.POINTER(_f), C.POINTER(_f)]),
+    "ccu_debug_layout_lookup": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -98,6 +100,18 @@ def check(rc: int):
 
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def layout_lookup(tree: np.ndarray, depth: int, xyz: np.ndarray):
+    """Host-only: what the commit-time traversal layouts answer for the voxels `xyz` (count x 3).  Returns a dict with
+    wide_value / wide_level (value-carrying layout) and air_solid / air_level (march layout)."""
+    tree = np.ascontiguousarray(tree, dtype=np.int32)
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32).reshape(-1, 3)
+    n = xyz.shape[0]
+    out = {k: np.empty(n, dtype=np.int32) for k in ("wide_value", "wide_level", "air_solid", "air_level")}
+    check(load().ccu_debug_layout_lookup(_ptr(tree), tree.size, depth, _ptr(xyz), n, _ptr(out["wide_value"]), _ptr(out["wide_level"]),
+                                         _ptr(out["air_solid"]), _ptr(out["air_level"])))
+    return out
 
 
 def device_count() -> int:
@@ -254,6 +268,12 @@ class Context:
         out = np.empty(w * h, np.int32)
         check(self._lib.ccu_preview(self._h, _ptr(out)))
         return out
+
+    def bench_gather(self, array_bytes: int, dependent: bool = False):
+        """Random 32-byte-sector gather microbenchmark: returns (GB/s of sectors, ns per load per thread)."""
+        gbs, ns = C.c_float(), C.c_float()
+        check(self._lib.ccu_bench_gather(self._h, int(array_bytes), 1 if dependent else 0, C.byref(gbs), C.byref(ns)))
+        return float(gbs.value), float(ns.value)
 
     def last_kernel_ms(self) -> float:
         ms = C.c_float()

@@ -120,6 +120,16 @@ int ccu_preview(ccu_ctx *ctx, int32_t *argb);
 int ccu_last_kernel_ms(ccu_ctx *ctx, float *ms);          /* CUDA-event time of the last render_passes / first_hit launch(es) */
 int ccu_launch_count(ccu_ctx *ctx, int64_t *launches);    /* kernels launched by this context so far */
 int ccu_scene_device_bytes(ccu_ctx *ctx, int64_t *bytes); /* HBM held by the committed scene */
+/* Memory-system denominators for this path's roofline (dependent 32-byte-sector gathers): random 16-byte
+ * L2 loads over an array of `array_bytes` (4 MB = L2 resident, 1 GB = HBM resident); dependent = 1 walks a pointer chain
+ * (ns_per_load = latency of one dependent gather), 0 issues independent loads (gbytes_per_s = sector bandwidth). */
+int ccu_bench_gather(ccu_ctx *ctx, int64_t array_bytes, int32_t dependent, float *gbytes_per_s, float *ns_per_load);
+/* Host-only (no CUDA call): what the two commit-time traversal layouts built from `tree` answer for `count` voxels
+ * (xyz = count x 3 ints): the value-carrying layout's leaf value / level (-1 / -1 when a leaf value cannot be encoded)
+ * and the march ("air") layout's not-air flag / air-leaf level (-1 when not air).  Both must agree with the reference's
+ * root descent (octree.h:81-88, ClSceneLoader.java:56-59 numbering); used by the CPU test-suite. */
+int ccu_debug_layout_lookup(const int32_t *tree, int64_t n, int32_t depth, const int32_t *xyz, int64_t count, int32_t *wide_value,
+                            int32_t *wide_level, int32_t *air_solid, int32_t *air_level);
 
 #ifdef __cplusplus
 }

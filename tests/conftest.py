@@ -36,6 +36,10 @@ def scenes():
                 cache[name] = S.mixed_test_scene()
             elif name == "indoor":
                 cache[name] = S.indoor_scene(64, 128, 72)
+            elif name == "large512":
+                cache[name] = S.large_world_scene(512, 64, 512, 160, 90)     # depth 9: top table too large for shared memory
+            elif name == "large2048":
+                cache[name] = S.large_world_scene(2048, 32, 2048, 128, 72)   # depth 11 (BASELINE config 5 shape)
             elif name == "entities":
                 cache[name] = S.entity_scene(128, 160, 90, n_world=96, n_actor=8, subdiv=1)
             else:

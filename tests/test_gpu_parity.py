@@ -11,7 +11,7 @@ from conftest import load_scene
 
 pytestmark = pytest.mark.gpu
 
-ALL = ["tiny8", "terrain64", "terrain128", "terrain256", "terrain256_nosun", "decorated", "mixed", "indoor", "entities"]
+ALL = ["tiny8", "terrain64", "terrain128", "terrain256", "terrain256_nosun", "decorated", "mixed", "indoor", "entities", "large512"]
 
 
 def _bits(a):
@@ -52,6 +52,32 @@ def test_render_bit_exact(name, kernel, scenes, cuda_ctx):
     bad = _bits(got) != _bits(ref)
     assert not bad.any(), f"{name}: {bad.sum()} of {bad.size} floats differ; max abs diff {np.abs(got - ref).max()}"
     assert np.isfinite(got).all() and got.max() > 0
+
+
+def test_render_depth11_world(scenes, cuda_ctx):
+    """BASELINE config 5 shape: a depth-11 octree (top table in global memory, three node levels below it)."""
+    import oracle
+    p = scenes("large2048")
+    load_scene(cuda_ctx, p)
+    seeds = pass_seeds(3)
+    cuda_ctx.render_passes(seeds)
+    got, _ = cuda_ctx.render_read()
+    ref = oracle.Oracle(p).render(seeds)
+    assert np.array_equal(_bits(got), _bits(ref))
+    assert got.max() > 0
+
+
+def test_render_top_table_in_global_memory(scenes, cuda_ctx, monkeypatch):
+    """The default kernel with its shared-memory staging of the top table switched off gives the same image."""
+    import oracle
+    p = scenes("terrain64")
+    seeds = pass_seeds(4)
+    ref = oracle.Oracle(p).render(seeds)
+    monkeypatch.setenv("CCU_NO_TOPS", "1")
+    load_scene(cuda_ctx, p)
+    cuda_ctx.render_passes(seeds)
+    got, _ = cuda_ctx.render_read()
+    assert np.array_equal(_bits(got), _bits(ref))
 
 
 def test_render_split_batches_equals_one_batch(scenes, cuda_ctx):
