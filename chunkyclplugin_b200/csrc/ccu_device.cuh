@@ -36,6 +36,12 @@ struct DScene {
     const int *__restrict__ actor_bvh;
     const int *__restrict__ trigs;
     int world_bvh_empty, actor_bvh_empty;   // result of the bvh.h:23-32 probe, evaluated once at commit
+    // BVH stage layout (built at commit): 64-byte records {left box, right box, left ref, right ref, pad, pad} per inner
+    // node, 16-byte aligned triangle blocks {count, 0, 0, 0} + count x 20 words; ref >= 0 record, ref < 0: -(1 + block offset / 4)
+    const int4 *__restrict__ world_rec;
+    const int4 *__restrict__ actor_rec;
+    const int4 *__restrict__ tris2;
+    int world_root, actor_root;
     // atlas: RGBA8, tile-linear (16x16 texel tiles contiguous), clamp extents = image extents
     const uchar4 *__restrict__ atlas;
     int atlas_w, atlas_h, atlas_layers, atlas_tiles_x, atlas_tiles_y;

@@ -41,7 +41,11 @@ constexpr int Q_SLOTS = Q_ROWS * 32;
 constexpr int Q_MW = (Q_ROWS + 31) / 32;   // mask words per stage and column
 static_assert(Q_ROWS >= 1 && Q_ROWS <= 64, "at most two mask words per stage and column");
 
-enum QStage : int { QS_MARCH = 0, QS_BLOCK, QS_EXIT, QS_BOUNCE, QS_END, QS_COUNT };
+// QS_BVH / QS_SHADE exist only in the kernels built for scenes with entity BVHs (HAS_BVH): there the BVH traversal runs as
+// a stage of its own between the octree part of closestIntersect (BLOCK / EXIT) and the shading (SHADE); without BVHs
+// BLOCK / EXIT shade directly.
+enum QStage : int { QS_MARCH = 0, QS_BLOCK, QS_EXIT, QS_BOUNCE, QS_END, QS_BVH, QS_SHADE, QS_COUNT_BVH };
+constexpr int QS_COUNT = QS_BVH;   // stages of the kernels without BVHs
 
 // Slot fields.  The running mean stays in the accumulation buffer (read-modify-write per sample, L2 only); the
 // surface point of the current hit is the origin of the shadow ray and lives in QF_O*.
@@ -49,23 +53,30 @@ enum QField : int {
     QF_GID = 0, QF_META, QF_RNG, QF_COLX, QF_COLY, QF_COLZ, QF_THRX, QF_THRY, QF_THRZ,
     QF_SNX, QF_SNY, QF_SNZ, QF_SHW,
     QF_OX, QF_OY, QF_OZ, QF_DX, QF_DY, QF_DZ, QF_IX, QF_IY, QF_IZ, QF_T, QF_LIMIT, QF_STEPS,
-    QF_COUNT
+    QF_COUNT,
+    // HAS_BVH only: the closest hit so far while the ray is in the BVH / SHADE stages.  Its distance, emittance and normal.x
+    // re-use the march fields of the (finished) ray: QF_LIMIT, QF_T, QF_STEPS.
+    QF_HNY = QF_COUNT, QF_HNZ, QF_HCX, QF_HCY, QF_HCZ,
+    QF_COUNT_BVH,
+    QF_HDIST = QF_LIMIT, QF_HEM = QF_T, QF_HNX = QF_STEPS
 };
 // QF_META: pass (bits 0..15) | ray depth (bits 16..23) | flags
 constexpr uint32_t QM_SHADOW = 1u << 24;     // the ray in flight is the sun-sampling shadow ray of the current surface
 constexpr uint32_t QM_NEEDPIX = 1u << 25;    // the slot holds no pixel (initial state)
+constexpr uint32_t QM_HIT = 1u << 26;        // BVH / SHADE stages: the ray has a hit (QF_H* valid)
 
 constexpr int Q_TOP_WORDS = 4096;            // top tables up to 16^3 cells are staged in shared memory
-constexpr int Q_MASK_WORDS = QS_COUNT * Q_MW * 32;
-constexpr int Q_SMEM_WORDS = QF_COUNT * Q_SLOTS + Q_MASK_WORDS + 32;   // + control words: live, tile lock / base / used
-constexpr int Q_SMEM_BYTES = Q_SMEM_WORDS * 4;
-constexpr int Q_SMEM_BYTES_TOP = (Q_SMEM_WORDS + Q_TOP_WORDS) * 4;
+__host__ __device__ constexpr int q_fields(bool bvh) { return bvh ? (int)QF_COUNT_BVH : (int)QF_COUNT; }
+__host__ __device__ constexpr int q_stages(bool bvh) { return bvh ? (int)QS_COUNT_BVH : (int)QS_COUNT; }
+__host__ __device__ constexpr int q_mask_words(bool bvh) { return q_stages(bvh) * Q_MW * 32; }
+// slot fields + work masks + control words (live, tile lock / base / used) [+ the staged top table]
+__host__ __device__ constexpr int q_smem_bytes(bool bvh, bool tops) { return (q_fields(bvh) * Q_SLOTS + q_mask_words(bvh) + 32 + (tops ? Q_TOP_WORDS : 0)) * 4; }
 
 #ifdef CCU_Q_STATS
 // debug counters (build with -DCCU_Q_STATS): [2*st] = executions of stage st, [2*st+1] = lanes that had a slot;
 // [10] march iterations, [11] lanes in flight summed over iterations, [12] scheduler rounds that found no work,
 // [13] march yields, [14] pop attempts, [15] pop retries
-__device__ unsigned long long g_qstats[16];
+__device__ unsigned long long g_qstats[32];   // [16] BVH stage entries, [18] BVH steps, [19] walking lanes, [20] leaf turns, [21] leaf lanes, [22] SHADE runs, [23] lanes
 #define QSTAT(i, v) do { const unsigned long long v_ = (unsigned long long)(v); if ((threadIdx.x & 31) == 0) atomicAdd(&g_qstats[i], v_); } while (0)
 #define QSTAT_LANE(i, v) atomicAdd(&g_qstats[i], (unsigned long long)(v))
 #else
@@ -77,6 +88,8 @@ struct QueueParams {
     WaveParams w;
     int yield_below;   // MARCH: consider switching stage once fewer lanes than this are busy
     int refill_min;    // MARCH: hand over / refill once this many lanes hold a finished ray
+    int leaf_min;      // BVH: process leaves once this many walks wait at one
+    int bvh_warps;     // scheduler: only warps 0 .. bvh_warps-1 run the BVH stage
     int march_bias;    // scheduler: warps of sub-partitions 0..2 count MARCH columns +bias, warps of sub-partition 3 -bias
 };
 
@@ -206,7 +219,8 @@ __device__ __forceinline__ void q_load_lean(const uint32_t *F, int slot, LeanRay
     lean_prepare(r);
 }
 
-// MARCH
+// MARCH (NST = number of stages of this kernel)
+template <int NST>
 __device__ __forceinline__ void q_stage_march(const DScene &s, const unsigned *__restrict__ top, uint32_t *F, unsigned *mask, int lane,
                                               int yield_below, int refill_min) {
     const unsigned full = 0xffffffffu;
@@ -239,7 +253,7 @@ __device__ __forceinline__ void q_stage_march(const DScene &s, const unsigned *_
                 if (recheck == 0) {
                     int best = 0;
 #pragma unroll
-                    for (int st = QS_BLOCK; st < QS_COUNT; st++) best = max(best, __popc(__ballot_sync(full, q_has_work(mask, st, lane))));
+                    for (int st = QS_BLOCK; st < NST; st++) best = max(best, __popc(__ballot_sync(full, q_has_work(mask, st, lane))));
                     if (best > busy) { QSTAT(13, 1); break; }
                     recheck = 4;
                 }
@@ -260,8 +274,55 @@ __device__ __forceinline__ void q_stage_march(const DScene &s, const unsigned *_
     }
 }
 
-// BLOCK (kind_block = true) and EXIT (false): the rest of closestIntersect (kernel.h:14-24) and what follows it in
-// rayTracer.cl:93-106.  kind_block is warp-uniform.
+// What follows closestIntersect in rayTracer.cl:93-106 for a ray whose closest hit is known: sky for a miss
+// (kernel.h:26-31), otherwise the surface response (kernel.h:33-44) and the sun sampling ray (sky.h:68-93).
+__device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *mask, int lane, int row, float3 o, float3 d, float distance,
+                                        bool ray_hit, const Surf &hit) {
+    const int slot = row * 32 + lane;
+    const uint32_t meta = QU(QF_META) & ~QM_HIT;
+    const bool shadow = (meta & QM_SHADOW) != 0;
+    if (!ray_hit) {
+        // kernel.h:26-31 with emittance 1 (path segment) or |d.n| (shadow ray)
+        float3 throughput = f3(QFL(QF_THRX), QFL(QF_THRY), QFL(QF_THRZ));
+        float3 color = f3(QFL(QF_COLX), QFL(QF_COLY), QFL(QF_COLZ));
+        float3 sky = sky_radiance(s, d);
+        color = color + (sky * throughput) * (shadow ? QFL(QF_SHW) : 1.0f);
+        QFL(QF_COLX) = color.x; QFL(QF_COLY) = color.y; QFL(QF_COLZ) = color.z;
+        q_push(mask, shadow ? QS_BOUNCE : QS_END, lane, row);
+    } else if (shadow) {
+        q_push(mask, QS_BOUNCE, lane, row);
+    } else {
+        // kernel.h:20-22 + applyRayColor kernel.h:33-44
+        float3 throughput = f3(QFL(QF_THRX), QFL(QF_THRY), QFL(QF_THRZ));
+        float3 color = f3(QFL(QF_COLX), QFL(QF_COLY), QFL(QF_COLZ));
+        float3 surf_point = o + d * (distance - CCU_OFFSET);
+        float3 col = f3(hit.color.x, hit.color.y, hit.color.z);
+        throughput = throughput * col;
+        color = color + (col * (hit.emittance * s.emitter_scale)) * throughput;
+        QFL(QF_THRX) = throughput.x; QFL(QF_THRY) = throughput.y; QFL(QF_THRZ) = throughput.z;
+        QFL(QF_COLX) = color.x; QFL(QF_COLY) = color.y; QFL(QF_COLZ) = color.z;
+        QFL(QF_SNX) = hit.normal.x; QFL(QF_SNY) = hit.normal.y; QFL(QF_SNZ) = hit.normal.z;
+        if (s.sun_flags & 1) {
+            uint32_t rng = QU(QF_RNG);
+            float x1 = rng_float(rng);
+            float x2 = rng_float(rng);
+            QU(QF_RNG) = rng;
+            float3 sd = sun_sample_direction(s, x1, x2);
+            QFL(QF_SHW) = fabsf(dot3(sd, hit.normal));
+            QU(QF_META) = meta | QM_SHADOW;
+            // the shadow ray starts at the surface point and inherits the surface hit's distance as its limit (SURVEY Q4)
+            March m;
+            const bool entered = march_begin(s, m, surf_point, sd, distance);
+            q_store_ray(F, mask, lane, row, m, entered);
+        } else {
+            QFL(QF_OX) = surf_point.x; QFL(QF_OY) = surf_point.y; QFL(QF_OZ) = surf_point.z;
+            q_push(mask, QS_BOUNCE, lane, row);
+        }
+    }
+}
+
+// BLOCK (kind_block = true) and EXIT (false): the octree part of closestIntersect (kernel.h:14-16) is finished here;
+// without BVHs the ray is shaded right away, with BVHs it goes to the BVH stage.  kind_block is warp-uniform.
 template <bool HAS_BVH>
 __device__ __forceinline__ void q_stage_resolve(const DScene &s, uint32_t *F, unsigned *mask, int lane, const bool kind_block) {
     const int row = q_pop(mask, kind_block ? QS_BLOCK : QS_EXIT, lane);
@@ -290,49 +351,198 @@ __device__ __forceinline__ void q_stage_resolve(const DScene &s, uint32_t *F, un
         }
         ray_hit = true;
     }
-    float distance = ray_hit ? hit_t : m.limit;
+    const float distance = ray_hit ? hit_t : m.limit;
     if (HAS_BVH) {
-        int kind = 0;
-        if (bvh_pair(s, m.o, m.d, distance, hit, kind)) ray_hit = true;
-    }
-    const uint32_t meta = QU(QF_META);
-    const bool shadow = (meta & QM_SHADOW) != 0;
-    if (!ray_hit) {
-        // kernel.h:26-31 with emittance 1 (path segment) or |d.n| (shadow ray)
-        float3 throughput = f3(QFL(QF_THRX), QFL(QF_THRY), QFL(QF_THRZ));
-        float3 color = f3(QFL(QF_COLX), QFL(QF_COLY), QFL(QF_COLZ));
-        float3 sky = sky_radiance(s, m.d);
-        color = color + (sky * throughput) * (shadow ? QFL(QF_SHW) : 1.0f);
-        QFL(QF_COLX) = color.x; QFL(QF_COLY) = color.y; QFL(QF_COLZ) = color.z;
-        q_push(mask, shadow ? QS_BOUNCE : QS_END, lane, row);
-    } else if (shadow) {
-        q_push(mask, QS_BOUNCE, lane, row);
-    } else {
-        // kernel.h:20-22 + applyRayColor kernel.h:33-44
-        float3 throughput = f3(QFL(QF_THRX), QFL(QF_THRY), QFL(QF_THRZ));
-        float3 color = f3(QFL(QF_COLX), QFL(QF_COLY), QFL(QF_COLZ));
-        float3 surf_point = m.o + m.d * (distance - CCU_OFFSET);
-        float3 col = f3(hit.color.x, hit.color.y, hit.color.z);
-        throughput = throughput * col;
-        color = color + (col * (hit.emittance * s.emitter_scale)) * throughput;
-        QFL(QF_THRX) = throughput.x; QFL(QF_THRY) = throughput.y; QFL(QF_THRZ) = throughput.z;
-        QFL(QF_COLX) = color.x; QFL(QF_COLY) = color.y; QFL(QF_COLZ) = color.z;
-        QFL(QF_SNX) = hit.normal.x; QFL(QF_SNY) = hit.normal.y; QFL(QF_SNZ) = hit.normal.z;
-        if (s.sun_flags & 1) {
-            uint32_t rng = QU(QF_RNG);
-            float x1 = rng_float(rng);
-            float x2 = rng_float(rng);
-            QU(QF_RNG) = rng;
-            float3 d = sun_sample_direction(s, x1, x2);
-            QFL(QF_SHW) = fabsf(dot3(d, hit.normal));
-            QU(QF_META) = meta | QM_SHADOW;
-            // the shadow ray starts at the surface point and inherits the surface hit's distance as its limit (SURVEY Q4)
-            const bool entered = march_begin(s, m, surf_point, d, distance);
-            q_store_ray(F, mask, lane, row, m, entered);
-        } else {
-            QFL(QF_OX) = surf_point.x; QFL(QF_OY) = surf_point.y; QFL(QF_OZ) = surf_point.z;
-            q_push(mask, QS_BOUNCE, lane, row);
+        // the march fields of the finished ray now carry the closest hit so far
+        QFL(QF_HDIST) = distance;
+        if (ray_hit) {
+            QFL(QF_HEM) = hit.emittance;
+            QFL(QF_HNX) = hit.normal.x; QFL(QF_HNY) = hit.normal.y; QFL(QF_HNZ) = hit.normal.z;
+            QFL(QF_HCX) = hit.color.x; QFL(QF_HCY) = hit.color.y; QFL(QF_HCZ) = hit.color.z;
         }
+        const uint32_t meta = QU(QF_META);
+        QU(QF_META) = ray_hit ? (meta | QM_HIT) : (meta & ~QM_HIT);
+        q_push(mask, QS_BVH, lane, row);
+    } else {
+        q_shade(s, F, mask, lane, row, m.o, m.d, distance, ray_hit, hit);
+    }
+}
+
+// SHADE (HAS_BVH kernels): closestIntersect is complete (kernel.h:17-22)
+__device__ __forceinline__ void q_stage_shade(const DScene &s, uint32_t *F, unsigned *mask, int lane) {
+    const int row = q_pop(mask, QS_SHADE, lane);
+    QSTAT(22, 1); QSTAT(23, __popc(__ballot_sync(0xffffffffu, row >= 0)));
+    if (row < 0) return;
+    const int slot = row * 32 + lane;
+    const float3 o = f3(QFL(QF_OX), QFL(QF_OY), QFL(QF_OZ));
+    const float3 d = f3(QFL(QF_DX), QFL(QF_DY), QFL(QF_DZ));
+    const bool ray_hit = (QU(QF_META) & QM_HIT) != 0;
+    Surf hit;
+    hit.normal = f3(QFL(QF_HNX), QFL(QF_HNY), QFL(QF_HNZ));
+    hit.color = make_float4(QFL(QF_HCX), QFL(QF_HCY), QFL(QF_HCZ), 0.0f);
+    hit.emittance = QFL(QF_HEM);
+    q_shade(s, F, mask, lane, row, o, d, QFL(QF_HDIST), ray_hit, hit);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// BVH stage: bvh.h:22-113 for the world BVH, then the actor BVH (kernel.h:17-18), on the commit-time layout
+// ------------------------------------------------------------------------------------------------------
+// Triangle_intersect (primitives.h:335-409) on an aligned 20-word record
+__device__ __forceinline__ float triangle_hit_aligned(const int4 *__restrict__ t, float distance, float3 origin, float3 dir, float3 &normal,
+                                                      float &ou, float &ov, int &material) {
+    const int4 q0 = __ldg(t), q1 = __ldg(t + 1);
+    const int flags = q0.x;
+    const float3 e1 = f3(i2f(q0.y), i2f(q0.z), i2f(q0.w));
+    const float3 e2 = f3(i2f(q1.x), i2f(q1.y), i2f(q1.z));
+    float3 pvec = cross3(dir, e2);
+    float det = dot3(e1, pvec);
+    if ((flags >> 8) & 1) {
+        if (det > -CCU_EPS && det < CCU_EPS) return nanf_();
+    } else if (det > -CCU_EPS) {
+        return nanf_();
+    }
+    float recip = 1.0f / det;
+    const int4 q2 = __ldg(t + 2);
+    float3 o = f3(i2f(q1.w), i2f(q2.x), i2f(q2.y));
+    float3 tvec = origin - o;
+    float u = dot3(tvec, pvec) * recip;
+    if (u < 0 || u > 1) return nanf_();
+    float3 qvec = cross3(tvec, e1);
+    float v = dot3(dir, qvec) * recip;
+    if (v < 0 || (u + v) > 1) return nanf_();
+    float tt = dot3(e2, qvec) * recip;
+    if (tt > CCU_EPS && tt < distance) {
+        const int4 q3 = __ldg(t + 3), q4 = __ldg(t + 4);
+        float w = 1.0f - u - v;
+        ou = (i2f(q3.y) * u + i2f(q3.w) * v) + i2f(q4.y) * w;
+        ov = (i2f(q3.z) * u + i2f(q4.x) * v) + i2f(q4.z) * w;
+        normal = f3(i2f(q2.z), i2f(q2.w), i2f(q3.x));
+        material = q4.w;
+        return tt;
+    }
+    return nanf_();
+}
+
+struct BvhWalk {
+    float3 o, d, inv;
+    float dist;        // closest hit so far (record->distance)
+    Surf hit;          // its surface, valid when `any`
+    bool any;          // a triangle was accepted during this stage
+    int ref;           // node to visit next: >= 0 inner record, < 0 leaf block
+    int sp;            // entries on the stack
+    int phase;         // 0 = world BVH, 1 = actor BVH, 2 = finished
+};
+
+// start the next non-empty BVH (kernel.h:17-18: world, then actor)
+__device__ __forceinline__ void bvh_next_phase(const DScene &s, BvhWalk &b) {
+    b.sp = 0;
+    for (;;) {
+        b.phase++;
+        if (b.phase == 0 && !s.world_bvh_empty) { b.ref = s.world_root; return; }
+        if (b.phase == 1 && !s.actor_bvh_empty) { b.ref = s.actor_root; return; }
+        if (b.phase >= 2) return;
+    }
+}
+
+__device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsigned *mask, int lane, int refill_min, int leaf_min) {
+    const unsigned full = 0xffffffffu;
+    int cur = -1;
+    BvhWalk b;
+    b.o = b.d = b.inv = f3(0, 0, 0);
+    b.dist = 0; b.any = false; b.ref = 0; b.sp = 0; b.phase = 2;
+    b.hit.normal = f3(0, 0, 0); b.hit.color = make_float4(0, 0, 0, 0); b.hit.emittance = 0;
+    int stack[64];      // bvh.h:38
+    int n_done = 0, n_fly = 0;
+    unsigned iter = 0;
+    for (;;) {
+        // hand-over / refill in batches; walks are long, so lanes without a slot also look for new work every 8 steps
+        if (n_done >= refill_min || n_fly == 0 || (++iter & 7u) == 0) {
+            if (cur < 0 || b.phase >= 2) {
+                if (cur >= 0) {
+                    const int slot = cur;
+                    if (b.any) {
+                        // record->material keeps its octree value (bvh.h:59-65); nothing downstream reads it
+                        QFL(QF_HDIST) = b.dist;
+                        QFL(QF_HEM) = b.hit.emittance;
+                        QFL(QF_HNX) = b.hit.normal.x; QFL(QF_HNY) = b.hit.normal.y; QFL(QF_HNZ) = b.hit.normal.z;
+                        QFL(QF_HCX) = b.hit.color.x; QFL(QF_HCY) = b.hit.color.y; QFL(QF_HCZ) = b.hit.color.z;
+                        QU(QF_META) |= QM_HIT;
+                    }
+                    q_push(mask, QS_SHADE, lane, cur >> 5);
+                }
+                const int row = q_pop(mask, QS_BVH, lane);
+                cur = row < 0 ? -1 : row * 32 + lane;
+                b.phase = 2;
+                if (cur >= 0) {
+                    const int slot = cur;
+                    b.o = f3(QFL(QF_OX), QFL(QF_OY), QFL(QF_OZ));
+                    b.d = f3(QFL(QF_DX), QFL(QF_DY), QFL(QF_DZ));
+                    b.inv = f3(QFL(QF_IX), QFL(QF_IY), QFL(QF_IZ));   // 1 / d, the same quotients bvh.h:40 computes
+                    b.dist = QFL(QF_HDIST);
+                    b.any = false;
+                    b.phase = -1;
+                    bvh_next_phase(s, b);
+                }
+            }
+            if (__ballot_sync(full, cur >= 0) == 0) return;
+        }
+        // One step per iteration, and only one kind of step for the whole warp: inner nodes while most walks are at
+        // inner nodes (walks that reached a leaf wait), leaves once enough walks wait at one.  Mixing both in one
+        // iteration would run each at a fraction of the lanes; the triangle tests are the expensive part.
+        const bool walking = cur >= 0 && b.phase < 2;
+        const int n_leaf = __popc(__ballot_sync(full, walking && b.ref < 0));
+        const int n_inner = __popc(__ballot_sync(full, walking && b.ref >= 0));
+        const bool leaf_turn = n_leaf >= leaf_min || n_inner == 0;
+        QSTAT(18, 1); QSTAT(19, n_leaf + n_inner); if (leaf_turn) { QSTAT(20, 1); QSTAT(21, n_leaf); }
+        bool pop = false;
+        if (leaf_turn) {
+            if (walking && b.ref < 0) {
+                // leaf: bvh.h:52-67
+                const int4 *blk = s.tris2 + (-(b.ref + 1));
+                const int num = __ldg(blk).x;
+                for (int i = 0; i < num; i++) {
+                    float3 normal;
+                    float u, v;
+                    int material;
+                    const float dist = triangle_hit_aligned(blk + 1 + 5 * i, b.dist, b.o, b.d, normal, u, v, material);
+                    if (!is_nan(dist) && material_sample(s, material, b.hit, u, v)) {
+                        b.hit.normal = normal;
+                        b.dist = dist;
+                        b.any = true;
+                    }
+                }
+                pop = true;
+            }
+        } else if (walking && b.ref >= 0) {
+            // inner node: both children's boxes (bvh.h:73-108)
+            const int4 *r = (b.phase == 0 ? s.world_rec : s.actor_rec) + (size_t)b.ref * 4;
+            const int4 a0 = __ldg(r), a1 = __ldg(r + 1), a2 = __ldg(r + 2), a3 = __ldg(r + 3);
+            const Box b1 = {i2f(a0.x), i2f(a0.y), i2f(a0.z), i2f(a0.w), i2f(a1.x), i2f(a1.y)};
+            const Box b2 = {i2f(a1.z), i2f(a1.w), i2f(a2.x), i2f(a2.y), i2f(a2.z), i2f(a2.w)};
+            const float t1 = box_entry(b1, b.o, b.inv);
+            const float t2 = box_entry(b2, b.o, b.inv);
+            const bool miss1 = is_nan(t1) || t1 > b.dist;
+            const bool miss2 = is_nan(t2) || t2 > b.dist;
+            const int left = a3.x, right = a3.y;
+            if (miss1) {
+                if (miss2) pop = true;
+                else b.ref = right;
+            } else if (miss2) {
+                b.ref = left;
+            } else if (t1 < t2) {
+                stack[b.sp++] = right;
+                b.ref = left;
+            } else {
+                stack[b.sp++] = left;
+                b.ref = right;
+            }
+        }
+        if (pop) {
+            if (b.sp == 0) bvh_next_phase(s, b);
+            else b.ref = stack[--b.sp];
+        }
+        n_fly = __popc(__ballot_sync(full, cur >= 0 && b.phase < 2));
+        n_done = __popc(__ballot_sync(full, cur >= 0 && b.phase >= 2));
     }
 }
 
@@ -474,16 +684,18 @@ __device__ __forceinline__ void q_stage_end(const DScene &s, const WaveParams &w
 // TOPS: the top table of the air layout fits Q_TOP_WORDS and is staged in shared memory
 template <bool HAS_BVH, bool TOPS>
 __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_constant__ DScene s, const __grid_constant__ QueueParams qp) {
+    constexpr int NST = q_stages(HAS_BVH);
+    constexpr int MASK_WORDS = q_mask_words(HAS_BVH);
     extern __shared__ uint32_t q_mem[];
     uint32_t *F = q_mem;
-    unsigned *mask = q_mem + QF_COUNT * Q_SLOTS;
-    int *live = reinterpret_cast<int *>(mask + Q_MASK_WORDS);
-    unsigned *top_s = mask + Q_MASK_WORDS + 32;
+    unsigned *mask = q_mem + q_fields(HAS_BVH) * Q_SLOTS;
+    int *live = reinterpret_cast<int *>(mask + MASK_WORDS);
+    unsigned *top_s = mask + MASK_WORDS + 32;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < Q_SLOTS; i += blockDim.x) F[QF_META * Q_SLOTS + i] = QM_NEEDPIX;
-    for (int i = threadIdx.x; i < Q_MASK_WORDS; i += blockDim.x) {
+    for (int i = threadIdx.x; i < MASK_WORDS; i += blockDim.x) {
         const int st = i / (Q_MW * 32), word = (i / 32) % Q_MW;
         const int rows = min(32, Q_ROWS - 32 * word);
         mask[i] = st == QS_END ? (rows == 32 ? 0xffffffffu : ((1u << rows) - 1u)) : 0u;
@@ -505,11 +717,14 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
         // the stage with the most columns that have work
         int best = -1, best_n = 0;
 #pragma unroll
-        for (int st = 0; st < QS_COUNT; st++) {
+        for (int st = 0; st < NST; st++) {
             int n = __popc(__ballot_sync(full, q_has_work(mask, st, lane)));
             // Warps of one SM sub-partition share an instruction cache: three sub-partitions lean towards the (small)
             // march loop, the fourth towards the (large) shading stages.
             if (st == QS_MARCH && n > 0) n = max(1, n + ((threadIdx.x >> 5 & 3) == 3 ? -qp.march_bias : qp.march_bias));
+            // A BVH walk is long and cannot be parked (it has a stack): the last warps of the CTA never take BVH work, so
+            // that the short stages, which feed the walkers, are always served promptly.
+            if (HAS_BVH && st == QS_BVH && (int)(threadIdx.x >> 5) >= qp.bvh_warps) n = 0;
             if (n > best_n) { best_n = n; best = st; }
         }
         if (best < 0) {
@@ -519,11 +734,13 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
             continue;
         }
         switch (best) {
-            case QS_MARCH: QSTAT(0, 1); q_stage_march(s, top, F, mask, lane, qp.yield_below, qp.refill_min); break;
+            case QS_MARCH: QSTAT(0, 1); q_stage_march<NST>(s, top, F, mask, lane, qp.yield_below, qp.refill_min); break;
             case QS_BLOCK:
             case QS_EXIT: q_stage_resolve<HAS_BVH>(s, F, mask, lane, best == QS_BLOCK); break;
             case QS_BOUNCE: q_stage_bounce(s, F, mask, lane); break;
-            default: q_stage_end(s, qp.w, F, mask, live, lane); break;
+            case QS_END: q_stage_end(s, qp.w, F, mask, live, lane); break;
+            case QS_BVH: QSTAT(16, 1); if (HAS_BVH) q_stage_bvh(s, F, mask, lane, qp.refill_min, qp.leaf_min); break;
+            default: if (HAS_BVH) q_stage_shade(s, F, mask, lane); break;
         }
         __syncwarp();
     }

@@ -7,9 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <climits>
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/chunkycu.h"
@@ -238,6 +240,9 @@ struct ccu_ctx {
     // scene
     DevBuf<int> tree, block_palette, quad_models, aabb_models, mat_palette, trigs, world_bvh, actor_bvh, sun_words;
     std::vector<int> world_head, actor_head;    // first node of each BVH for the emptiness probe
+    std::vector<int> world_host, actor_host, trigs_host;   // kept for the commit-time BVH layout
+    DevBuf<int> world_rec, actor_rec, tris2;
+    int world_root = 0, actor_root = 0, use_bvh2 = 0;
     DevBuf<uchar4> atlas, sky;
     std::vector<int> tree_host;              // kept for the commit-time traversal layout
     DevBuf<unsigned> top, wide;
@@ -271,6 +276,8 @@ struct ccu_ctx {
     int yield_below = 16;
     int q_refill_min = 8;
     int q_march_bias = 4;
+    int q_leaf_min = 12;
+    int q_bvh_warps = 24;
     int blocks_per_sm = CCU_MIN_BLOCKS;
     int seeds_cap = 0;
     int window_spp = 0;
@@ -321,6 +328,11 @@ int fill_scene(ccu_ctx *c) {
     s.air_top = c->air_top.p;
     s.air_wide = c->air_wide.p;
     s.air_bits = c->air_bits.p;
+    s.world_rec = reinterpret_cast<const int4 *>(c->world_rec.p);
+    s.actor_rec = reinterpret_cast<const int4 *>(c->actor_rec.p);
+    s.tris2 = reinterpret_cast<const int4 *>(c->tris2.p);
+    s.world_root = c->world_root;
+    s.actor_root = c->actor_root;
     s.block_palette = c->block_palette.p;
     s.block_palette_len = (int)c->block_palette.n;
     s.quad_models = c->quad_models.p;
@@ -501,6 +513,60 @@ AirLayout build_air_layout(const int *tree, size_t n, int depth, int cl) {
     return b;
 }
 
+// Traversal layout of a packed BVH (PackedBvhNode.java:22-31: 7 ints per node, first child at node + 7, second child at
+// node[0]) for the BVH stage of ccu_queue.cuh: one 64-byte record per inner node holding BOTH children's boxes
+// (bvh.h:73-91 fetches exactly those at every inner node) and a reference per child, and 16-byte aligned triangle
+// blocks.  ref >= 0: record index; ref < 0: leaf, -(1 + offset of its block in `tris`, in units of 4 words).
+struct BvhLayout {
+    std::vector<int> rec;
+    int root = 0;
+    bool ok = true;
+};
+struct TriRepack {
+    std::vector<int> tris;                       // per leaf: {count, 0, 0, 0} + count x 20 words (PackedTriangle.java:46-78)
+    int add(const std::vector<int> &trigs, int prim, bool &ok) {
+        if (prim < 0 || (size_t)prim >= trigs.size()) { ok = false; return 0; }
+        const int count = trigs[(size_t)prim];
+        if (count < 0 || (size_t)prim + 1 + (size_t)count * 20 > trigs.size()) { ok = false; return 0; }
+        const int off = (int)(tris.size() / 4);
+        tris.push_back(count); tris.push_back(0); tris.push_back(0); tris.push_back(0);
+        tris.insert(tris.end(), trigs.begin() + prim + 1, trigs.begin() + prim + 1 + (size_t)count * 20);
+        return off;
+    }
+};
+
+int bvh_ref(const std::vector<int> &bvh, const std::vector<int> &trigs, size_t node, int depth, BvhLayout &b, TriRepack &tr,
+            std::unordered_map<int, int> &leaf_map) {
+    if (!b.ok) return -1;
+    if (node + 6 >= bvh.size() || depth > 256) { b.ok = false; return -1; }
+    const int head = bvh[node];
+    if (head <= 0) {
+        const int prim = -head;
+        auto it = leaf_map.find(prim);   // a leaf block referenced twice (both BVHs share the palette) is stored once
+        int off;
+        if (it != leaf_map.end()) {
+            off = it->second;
+        } else {
+            off = tr.add(trigs, prim, b.ok);
+            leaf_map.emplace(prim, off);
+        }
+        return -(1 + off);
+    }
+    const size_t left = node + 7, right = (size_t)head;
+    if (left + 6 >= bvh.size() || right + 6 >= bvh.size()) { b.ok = false; return -1; }
+    const size_t r = b.rec.size() / 16;
+    b.rec.resize(b.rec.size() + 16, 0);
+    for (int i = 0; i < 6; i++) {
+        b.rec[r * 16 + i] = bvh[left + 1 + i];
+        b.rec[r * 16 + 6 + i] = bvh[right + 1 + i];
+    }
+    const int rl = bvh_ref(bvh, trigs, left, depth + 1, b, tr, leaf_map);
+    const int rr = bvh_ref(bvh, trigs, right, depth + 1, b, tr, leaf_map);
+    b.rec[r * 16 + 12] = rl;
+    b.rec[r * 16 + 13] = rr;
+    return (int)r;
+}
+
 WideLayout build_wide_layout(const int *tree, size_t n, int depth) {
     WideLayout b;
     int cl = std::max(depth - 7, 4);
@@ -581,6 +647,8 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     if (const char *e = getenv("CCU_WAIT_LANES")) c->wait_lanes = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_REFILL_MIN")) c->refill_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_EXIT_IDLE")) c->exit_idle = std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("CCU_Q_BVH_WARPS")) c->q_bvh_warps = std::max(1, std::min(64, atoi(e)));
+    if (const char *e = getenv("CCU_Q_LEAF_MIN")) c->q_leaf_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_Q_MARCH_BIAS")) c->q_march_bias = std::max(-32, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_Q_REFILL_MIN")) c->q_refill_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_YIELD_BELOW")) c->yield_below = std::max(0, std::min(33, atoi(e)));
@@ -593,10 +661,10 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES_TOP);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES_TOP);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, q_smem_bytes(true, true));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, q_smem_bytes(false, true));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, q_smem_bytes(true, false));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, q_smem_bytes(false, false));
     if (e == cudaSuccess) e = cudaMalloc(&c->unorm, 256 * sizeof(float));
     if (e == cudaSuccess) {
         k_unorm_table<<<1, 256, 0, c->stream>>>(c->unorm);
@@ -619,7 +687,7 @@ int ccu_ctx_destroy(ccu_ctx *c) {
         std::lock_guard<std::mutex> lk(c->mu);
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
-        c->tree.release(); c->top.release(); c->wide.release(); c->air_top.release(); c->air_wide.release(); c->air_bits.release(); c->block_palette.release(); c->quad_models.release(); c->aabb_models.release();
+        c->tree.release(); c->top.release(); c->wide.release(); c->air_top.release(); c->air_wide.release(); c->air_bits.release(); c->world_rec.release(); c->actor_rec.release(); c->tris2.release(); c->block_palette.release(); c->quad_models.release(); c->aabb_models.release();
         c->mat_palette.release(); c->trigs.release(); c->world_bvh.release(); c->actor_bvh.release();
         c->sun_words.release(); c->atlas.release(); c->sky.release(); c->rays.release(); c->sun_basis.release();
         if (c->accum) cudaFree(c->accum);
@@ -656,15 +724,19 @@ int ccu_scene_set_block_palette(ccu_ctx *c, const int32_t *w, int64_t n) { retur
 int ccu_scene_set_quad_models(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->quad_models, w, n, "ccu_scene_set_quad_models"); }
 int ccu_scene_set_aabb_models(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->aabb_models, w, n, "ccu_scene_set_aabb_models"); }
 int ccu_scene_set_material_palette(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->mat_palette, w, n, "ccu_scene_set_material_palette"); }
-int ccu_scene_set_triangles(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->trigs, w, n, "ccu_scene_set_triangles"); }
+int ccu_scene_set_triangles(ccu_ctx *c, const int32_t *w, int64_t n) {
+    int rc = upload_words(c, c->trigs, w, n, "ccu_scene_set_triangles");
+    if (rc == CCU_OK) c->trigs_host.assign(w, w + n);
+    return rc;
+}
 int ccu_scene_set_world_bvh(ccu_ctx *c, const int32_t *w, int64_t n) {
     int rc = upload_words(c, c->world_bvh, w, n, "ccu_scene_set_world_bvh");
-    if (rc == CCU_OK) c->world_head.assign(w, w + std::min<int64_t>(n, 7));
+    if (rc == CCU_OK) { c->world_head.assign(w, w + std::min<int64_t>(n, 7)); c->world_host.assign(w, w + n); }
     return rc;
 }
 int ccu_scene_set_actor_bvh(ccu_ctx *c, const int32_t *w, int64_t n) {
     int rc = upload_words(c, c->actor_bvh, w, n, "ccu_scene_set_actor_bvh");
-    if (rc == CCU_OK) c->actor_head.assign(w, w + std::min<int64_t>(n, 7));
+    if (rc == CCU_OK) { c->actor_head.assign(w, w + std::min<int64_t>(n, 7)); c->actor_host.assign(w, w + n); }
     return rc;
 }
 
@@ -754,8 +826,9 @@ int ccu_scene_commit(ccu_ctx *c) {
     if (!c->quad_models.p) CU(c->quad_models.upload(&zero, 0, c->stream));
     if (!c->aabb_models.p) CU(c->aabb_models.upload(&zero, 0, c->stream));
     if (!c->trigs.p) CU(c->trigs.upload(&zero, 0, c->stream));
-    if (!c->world_bvh.p) { CU(c->world_bvh.upload(&zero, 0, c->stream)); c->world_head.clear(); }
-    if (!c->actor_bvh.p) { CU(c->actor_bvh.upload(&zero, 0, c->stream)); c->actor_head.clear(); }
+    if (!c->trigs.p || c->trigs.n == 0) c->trigs_host.clear();
+    if (!c->world_bvh.p) { CU(c->world_bvh.upload(&zero, 0, c->stream)); c->world_head.clear(); c->world_host.clear(); }
+    if (!c->actor_bvh.p) { CU(c->actor_bvh.upload(&zero, 0, c->stream)); c->actor_head.clear(); c->actor_host.clear(); }
     // traversal layout: dense top table + 64-ary nodes (two octree levels per load); falls back to the plain
     // reference layout if a leaf value cannot be encoded
     {
@@ -771,6 +844,23 @@ int ccu_scene_commit(ccu_ctx *c) {
         CU(c->air_top.upload(al.top.data(), al.top.size(), c->stream));
         CU(c->air_wide.upload(al.wide.data(), al.wide.size(), c->stream));
         CU(c->air_bits.upload(al.bits.data(), al.bits.size(), c->stream));
+    }
+    // BVH stage layout (pair records + aligned triangle blocks); without it kernel 4 falls back to kernel 3 for BVH scenes
+    {
+        BvhLayout wb, ab;
+        TriRepack tr;
+        std::unordered_map<int, int> leaf_map;
+        const bool we = bvh_is_empty(c->world_head), ae = bvh_is_empty(c->actor_head);
+        if (!we) wb.root = bvh_ref(c->world_host, c->trigs_host, 0, 0, wb, tr, leaf_map);
+        if (!ae) ab.root = bvh_ref(c->actor_host, c->trigs_host, 0, 0, ab, tr, leaf_map);
+        c->use_bvh2 = (wb.ok && ab.ok) ? 1 : 0;
+        c->world_root = wb.root;
+        c->actor_root = ab.root;
+        if (c->use_bvh2) {
+            CU(c->world_rec.upload(wb.rec.data(), wb.rec.size(), c->stream));
+            CU(c->actor_rec.upload(ab.rec.data(), ab.rec.size(), c->stream));
+            CU(c->tris2.upload(tr.tris.data(), tr.tris.size(), c->stream));
+        }
     }
     // sun basis on the device
     if (!c->sun_basis.p) {
@@ -921,27 +1011,32 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
             qp.yield_below = c->yield_below;
             qp.refill_min = c->q_refill_min;
             qp.march_bias = c->q_march_bias;
+            qp.leaf_min = c->q_leaf_min;
+            qp.bvh_warps = c->q_bvh_warps;
             const bool tops = c->air_top.n <= (size_t)Q_TOP_WORDS && getenv("CCU_NO_TOPS") == nullptr;
             const int grid = c->sm_count, block = Q_WARPS * 32;
             if (!c->use_air) return fail(CCU_ESTATE, "ccu_render_passes: kernel 4 needs the air layout (malformed octree?)");
+            if (bvh && !c->use_bvh2) return fail(CCU_ESTATE, "ccu_render_passes: kernel 4 needs the BVH stage layout (malformed BVH?)");
             if (tops) {
-                if (bvh) k_render_queue<true, true><<<grid, block, Q_SMEM_BYTES_TOP, c->stream>>>(c->scene, qp);
-                else k_render_queue<false, true><<<grid, block, Q_SMEM_BYTES_TOP, c->stream>>>(c->scene, qp);
+                if (bvh) k_render_queue<true, true><<<grid, block, q_smem_bytes(true, true), c->stream>>>(c->scene, qp);
+                else k_render_queue<false, true><<<grid, block, q_smem_bytes(false, true), c->stream>>>(c->scene, qp);
             } else {
-                if (bvh) k_render_queue<true, false><<<grid, block, Q_SMEM_BYTES, c->stream>>>(c->scene, qp);
-                else k_render_queue<false, false><<<grid, block, Q_SMEM_BYTES, c->stream>>>(c->scene, qp);
+                if (bvh) k_render_queue<true, false><<<grid, block, q_smem_bytes(true, false), c->stream>>>(c->scene, qp);
+                else k_render_queue<false, false><<<grid, block, q_smem_bytes(false, false), c->stream>>>(c->scene, qp);
             }
 #ifdef CCU_Q_STATS
             {
                 cudaStreamSynchronize(c->stream);
-                unsigned long long st[16];
+                unsigned long long st[32];
                 cudaMemcpyFromSymbol(st, g_qstats, sizeof st);
                 const char *names[5] = {"march", "block", "exit", "bounce", "end"};
                 fprintf(stderr, "[qstats] ");
                 for (int i = 1; i < 5; i++) fprintf(stderr, "%s: %llu x %.1f lanes  ", names[i], st[2 * i], st[2 * i] ? (double)st[2 * i + 1] / st[2 * i] : 0.0);
                 fprintf(stderr, "\n[qstats] march stages %llu, iterations %llu x %.1f lanes in flight, yields %llu, idle rounds %llu, pops %llu retries %llu\n", st[0], st[10],
                         st[10] ? (double)st[11] / st[10] : 0.0, st[13], st[12], st[14], st[15]);
-                unsigned long long z[16] = {0};
+                fprintf(stderr, "[qstats] bvh stages %llu, steps %llu x %.1f walking lanes, leaf turns %llu x %.1f lanes, shade %llu x %.1f lanes\n", st[16], st[18],
+                        st[18] ? (double)st[19] / st[18] : 0.0, st[20], st[20] ? (double)st[21] / st[20] : 0.0, st[22], st[22] ? (double)st[23] / st[22] : 0.0);
+                unsigned long long z[32] = {0};
                 cudaMemcpyToSymbol(g_qstats, z, sizeof z);
             }
 #endif
@@ -1148,7 +1243,7 @@ int ccu_launch_count(ccu_ctx *c, int64_t *launches) {
 int ccu_scene_device_bytes(ccu_ctx *c, int64_t *bytes) {
     if (!c || !bytes) return fail(CCU_EINVAL, "ccu_scene_device_bytes: null argument");
     std::lock_guard<std::mutex> lk(c->mu);
-    *bytes = (int64_t)(c->tree.bytes() + c->top.bytes() + c->wide.bytes() + c->air_top.bytes() + c->air_wide.bytes() + c->air_bits.bytes() + c->block_palette.bytes() + c->quad_models.bytes() + c->aabb_models.bytes() + c->mat_palette.bytes() +
+    *bytes = (int64_t)(c->tree.bytes() + c->top.bytes() + c->wide.bytes() + c->air_top.bytes() + c->air_wide.bytes() + c->air_bits.bytes() + c->world_rec.bytes() + c->actor_rec.bytes() + c->tris2.bytes() + c->block_palette.bytes() + c->quad_models.bytes() + c->aabb_models.bytes() + c->mat_palette.bytes() +
                        c->trigs.bytes() + c->world_bvh.bytes() + c->actor_bvh.bytes() + c->atlas.bytes() + c->sky.bytes());
     return CCU_OK;
 }
