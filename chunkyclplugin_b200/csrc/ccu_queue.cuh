@@ -90,6 +90,7 @@ struct QueueParams {
     int refill_min;    // MARCH: hand over / refill once this many lanes hold a finished ray
     int leaf_min;      // BVH: process leaves once this many walks wait at one
     int bvh_warps;     // scheduler: only warps 0 .. bvh_warps-1 run the BVH stage
+    int march_warps;   // scheduler: only warps 0 .. march_warps-1 run the MARCH stage
     int march_bias;    // scheduler: warps of sub-partitions 0..2 count MARCH columns +bias, warps of sub-partition 3 -bias
 };
 
@@ -725,6 +726,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
             // A BVH walk is long and cannot be parked (it has a stack): the last warps of the CTA never take BVH work, so
             // that the short stages, which feed the walkers, are always served promptly.
             if (HAS_BVH && st == QS_BVH && (int)(threadIdx.x >> 5) >= qp.bvh_warps) n = 0;
+            if (st == QS_MARCH && (int)(threadIdx.x >> 5) >= qp.march_warps) n = 0;
             if (n > best_n) { best_n = n; best = st; }
         }
         if (best < 0) {

@@ -19,6 +19,7 @@
 #include "ccu_wavefront.cuh"
 #include "ccu_pool.cuh"
 #include "ccu_queue.cuh"
+#include "ccu_tonemap.cuh"
 
 using namespace ccu;
 
@@ -133,6 +134,12 @@ __global__ void __launch_bounds__(128) k_preview(const __grid_constant__ DScene 
         rgb[i] = f2i(floorf(q));
     }
     res[gid] = (int)(0xFF000000u | ((uint32_t)rgb[0] << 16) | ((uint32_t)rgb[1] << 8) | (uint32_t)rgb[2]);
+}
+
+// post_processing_filter.cl:5-51: one work-item per pixel
+__global__ void __launch_bounds__(256) k_tonemap(int n_pixels, float exposure, const double *__restrict__ input, int type, uint32_t *__restrict__ res) {
+    for (int gid = blockIdx.x * blockDim.x + threadIdx.x; gid < n_pixels; gid += gridDim.x * blockDim.x)
+        res[gid] = tonemap_pixel(input + (size_t)gid * 3, exposure, type);
 }
 
 __global__ void k_unorm_table(float *t) { t[threadIdx.x] = (float)threadIdx.x / 255.0f; }
@@ -278,6 +285,7 @@ struct ccu_ctx {
     int q_march_bias = 4;
     int q_leaf_min = 12;
     int q_bvh_warps = 24;
+    int q_march_warps = 22;
     int blocks_per_sm = CCU_MIN_BLOCKS;
     int seeds_cap = 0;
     int window_spp = 0;
@@ -647,6 +655,7 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     if (const char *e = getenv("CCU_WAIT_LANES")) c->wait_lanes = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_REFILL_MIN")) c->refill_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_EXIT_IDLE")) c->exit_idle = std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("CCU_Q_MARCH_WARPS")) c->q_march_warps = std::max(1, std::min(64, atoi(e)));
     if (const char *e = getenv("CCU_Q_BVH_WARPS")) c->q_bvh_warps = std::max(1, std::min(64, atoi(e)));
     if (const char *e = getenv("CCU_Q_LEAF_MIN")) c->q_leaf_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_Q_MARCH_BIAS")) c->q_march_bias = std::max(-32, std::min(32, atoi(e)));
@@ -1013,6 +1022,7 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
             qp.march_bias = c->q_march_bias;
             qp.leaf_min = c->q_leaf_min;
             qp.bvh_warps = c->q_bvh_warps;
+            qp.march_warps = c->q_march_warps;
             const bool tops = c->air_top.n <= (size_t)Q_TOP_WORDS && getenv("CCU_NO_TOPS") == nullptr;
             const int grid = c->sm_count, block = Q_WARPS * 32;
             if (!c->use_air) return fail(CCU_ESTATE, "ccu_render_passes: kernel 4 needs the air layout (malformed octree?)");
@@ -1245,6 +1255,36 @@ int ccu_scene_device_bytes(ccu_ctx *c, int64_t *bytes) {
     std::lock_guard<std::mutex> lk(c->mu);
     *bytes = (int64_t)(c->tree.bytes() + c->top.bytes() + c->wide.bytes() + c->air_top.bytes() + c->air_wide.bytes() + c->air_bits.bytes() + c->world_rec.bytes() + c->actor_rec.bytes() + c->tris2.bytes() + c->block_palette.bytes() + c->quad_models.bytes() + c->aabb_models.bytes() + c->mat_palette.bytes() +
                        c->trigs.bytes() + c->world_bvh.bytes() + c->actor_bvh.bytes() + c->atlas.bytes() + c->sky.bytes());
+    return CCU_OK;
+}
+
+int ccu_tonemap(ccu_ctx *c, int32_t width, int32_t height, float exposure, const double *input, int32_t type, int32_t *argb) {
+    if (!c || !input || !argb) return fail(CCU_EINVAL, "ccu_tonemap: null argument");
+    if (width <= 0 || height <= 0 || (int64_t)width * height > (1ll << 30)) return fail(CCU_EINVAL, "ccu_tonemap: bad canvas %dx%d", width, height);
+    if (type < 0 || type > 3) return fail(CCU_EINVAL, "ccu_tonemap: unknown filter %d (0 GAMMA, 1 TONEMAP1, 2 ACES, 3 HABLE)", type);
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    const size_t n = (size_t)width * height;
+    double *d_in = nullptr;
+    uint32_t *d_out = nullptr;
+    CU(cudaMalloc(&d_in, n * 3 * sizeof(double)));
+    cudaError_t e = cudaMalloc(&d_out, n * sizeof(uint32_t));
+    // the reference uploads the whole double buffer and reads the ARGB image back on every call (GpuPostProcessingFilter.java:43-61)
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, input, n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        cudaEventRecord(c->ev0, c->stream);
+        k_tonemap<<<c->sm_count * 8, 256, 0, c->stream>>>((int)n, exposure, d_in, type, d_out);
+        cudaEventRecord(c->ev1, c->stream);
+        c->timing_pending = true;
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(argb, d_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_in);
+    if (d_out) cudaFree(d_out);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? CCU_ENOMEM : CCU_ECUDA, "ccu_tonemap: %s", cudaGetErrorString(e));
+    stop_timer(c);
     return CCU_OK;
 }
 

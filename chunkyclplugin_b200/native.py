@@ -71,6 +71,7 @@ SYMBOLS = {
     "ccu_last_kernel_ms": (C.c_int, [_vp, C.POINTER(_f)]),
     "ccu_launch_count": (C.c_int, [_vp, C.POINTER(_i64)]),
     "ccu_scene_device_bytes": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "ccu_tonemap": (C.c_int, [_vp, _i32, _i32, _f, _vp, _i32, _vp]),
     "ccu_bench_gather": (C.c_int, [_vp, _i64, _i32, C.POINTER(_f), C.POINTER(_f)]),
     "ccu_debug_layout_lookup": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
 }
@@ -267,6 +268,15 @@ class Context:
         w, h = self._wh
         out = np.empty(w * h, np.int32)
         check(self._lib.ccu_preview(self._h, _ptr(out)))
+        return out
+
+    def tonemap(self, width: int, height: int, exposure: float, sample_buffer: np.ndarray, filter_type: int) -> np.ndarray:
+        """GpuPostProcessingFilter.processFrame: double sample buffer -> ARGB int[W*H]."""
+        inp = np.ascontiguousarray(sample_buffer, dtype=np.float64).reshape(-1)
+        if inp.size != width * height * 3:
+            raise ValueError("sample buffer must hold 3 doubles per pixel")
+        out = np.empty(width * height, dtype=np.int32)
+        check(self._lib.ccu_tonemap(self._h, width, height, C.c_float(exposure), _ptr(inp), filter_type, _ptr(out)))
         return out
 
     def bench_gather(self, array_bytes: int, dependent: bool = False):

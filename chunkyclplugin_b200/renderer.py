@@ -283,6 +283,43 @@ class CudaPreviewRenderer:
             ctx.render_end()
 
 
+# ----------------------------------------------------------------------------------------------------
+# tonemap/GpuPostProcessingFilter.java, ImposterCombinationGpuPostProcessingFilter.java, ChunkyCl.java:59-71
+# ----------------------------------------------------------------------------------------------------
+class BitmapImage:
+    """Stand-in for se.llbit.chunky.resources.BitmapImage: ARGB ints, row-major."""
+
+    def __init__(self, width: int, height: int):
+        self.width, self.height = width, height
+        self.data = np.zeros(width * height, dtype=np.int32)
+
+
+class GpuPostProcessingFilter:
+    """PostProcessingFilter that shadows one of Chunky's filters (same name / id) with the device kernel."""
+
+    class Filter:                                             # ImposterCombinationGpuPostProcessingFilter.java:11-16
+        GAMMA, TONEMAP1, ACES, HABLE = 0, 1, 2, 3
+
+    # ChunkyCl.java:59-62: which Chunky filter id each kernel type shadows
+    IMPOSTERS = {"GAMMA": Filter.GAMMA, "TONEMAP1": Filter.TONEMAP1, "TONEMAP2": Filter.ACES, "TONEMAP3": Filter.HABLE}
+
+    def __init__(self, filter_id: str, instance: Optional[RendererInstance] = None, name: Optional[str] = None,
+                 description: Optional[str] = None):
+        if filter_id not in self.IMPOSTERS:
+            raise KeyError(f"no device filter shadows {filter_id!r}")
+        self.id, self.filter = filter_id, self.IMPOSTERS[filter_id]
+        self.name = name or filter_id
+        self.description = description or filter_id
+        self.instance = instance or RendererInstance.get()
+
+    def getName(self): return self.name
+    def getDescription(self): return self.description
+    def getId(self): return self.id
+
+    def processFrame(self, width: int, height: int, input: np.ndarray, output: BitmapImage, exposure: float, task=None):   # :40-65
+        output.data[:] = self.instance.context.tonemap(width, height, float(exposure), input, self.filter)
+
+
 # reference-named aliases, so code written against the reference's class names reads the same
 ClSceneLoader = CudaSceneLoader
 ClCamera = CudaCamera

@@ -116,6 +116,11 @@ int ccu_first_hit(ccu_ctx *ctx, int32_t seed, int32_t *block, int32_t *face, int
 /* ---- preview: OpenClPreviewRenderer.java:47-115 (kernel rayTracer.cl:115-217), ARGB int[W*H] ----------------- */
 int ccu_preview(ccu_ctx *ctx, int32_t *argb);
 
+/* ---- post-processing filters: GpuPostProcessingFilter.processFrame (tonemap/GpuPostProcessingFilter.java:40-65), kernel
+ *      tonemap/include/post_processing_filter.cl:5-51.  input = Chunky's double sample buffer (3 per pixel), argb = int[W*H];
+ *      type: 0 GAMMA, 1 TONEMAP1, 2 ACES ("TONEMAP2"), 3 HABLE ("TONEMAP3") (ImposterCombinationGpuPostProcessingFilter.java:11-16) */
+int ccu_tonemap(ccu_ctx *ctx, int32_t width, int32_t height, float exposure, const double *input, int32_t type, int32_t *argb);
+
 /* ---- instrumentation ------------------------------------------------------------------------------------------ */
 int ccu_last_kernel_ms(ccu_ctx *ctx, float *ms);          /* CUDA-event time of the last render_passes / first_hit launch(es) */
 int ccu_launch_count(ccu_ctx *ctx, int64_t *launches);    /* kernels launched by this context so far */

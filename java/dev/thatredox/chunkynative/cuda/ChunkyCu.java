@@ -51,6 +51,7 @@ public final class ChunkyCu {
     private static final MethodHandle RENDER_MERGE = h("ccu_render_merge", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
     private static final MethodHandle RENDER_END = h("ccu_render_end", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle PREVIEW = h("ccu_preview", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle TONEMAP = h("ccu_tonemap", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_FLOAT, ADDRESS, JAVA_INT, ADDRESS));
 
     private ChunkyCu() {}
 
@@ -155,6 +156,16 @@ public final class ChunkyCu {
             try (Arena a = Arena.ofConfined()) {
                 MemorySegment out = a.allocate(JAVA_INT, argb.length);
                 check(call(PREVIEW, handle, out));
+                MemorySegment.copy(out, JAVA_INT, 0, argb, 0, argb.length);
+            }
+        }
+
+        /** GpuPostProcessingFilter.processFrame (tonemap/GpuPostProcessingFilter.java:40-65): filter = Filter.id (0..3). */
+        public void tonemap(int width, int height, double[] input, int[] argb, double exposure, int filter) {
+            try (Arena a = Arena.ofConfined()) {
+                MemorySegment in = a.allocateFrom(JAVA_DOUBLE, input);
+                MemorySegment out = a.allocate(JAVA_INT, argb.length);
+                check(call(TONEMAP, handle, width, height, (float) exposure, in, filter, out));
                 MemorySegment.copy(out, JAVA_INT, 0, argb, 0, argb.length);
             }
         }

@@ -169,3 +169,16 @@ def math_fn(fn: str, x: np.ndarray, y: Optional[np.ndarray] = None, libm: bool =
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def tonemap(width: int, height: int, exposure: float, sample_buffer: np.ndarray, filter_type: int, libm: bool = False,
+            threads: int = 0) -> np.ndarray:
+    """post_processing_filter.cl:5-51 on the CPU: double sample buffer -> ARGB int[W*H]."""
+    inp = np.ascontiguousarray(sample_buffer, dtype=np.float64).reshape(-1)
+    assert inp.size == width * height * 3
+    out = np.empty(width * height, dtype=np.int32)
+    rc = lib().oracle_tonemap(C.c_int(width), C.c_int(height), C.c_float(exposure), inp.ctypes.data_as(C.c_void_p), C.c_int(filter_type),
+                              out.ctypes.data_as(C.c_void_p), C.c_int(1 if libm else 0), C.c_int(threads))
+    if rc != 0:
+        raise ValueError("oracle_tonemap: bad arguments")
+    return out

@@ -16,6 +16,8 @@
  *   material.h:31-82  textureAtlas.h:10-28  sky.h:19-106  camera.h:8-32
  *   randomness.h:6-17 utils.h:6-27  wavefront.h:13-78  constants.h:4-5
  * Image sampling follows OpenCL 1.2 section 8.2.
+ * Tonemap filters (oracle_tonemap): /root/reference/src/main/opencl/tonemap/include/post_processing_filter.cl:5-51,
+ *   double.h:17-19, rgba.h:6-16; pinned against that kernel run on a B200 (tests/golden/clref_tonemap.npz).
  *
  * Arithmetic contract (shared with the CUDA build, see DESIGN.md "Arithmetic contract"):
  *   - every fp32 operation the reference writes out is a single IEEE-754 round-to-nearest operation, in
@@ -1030,3 +1032,109 @@ int oracle_num_threads(void) {
 #endif
 }
 int oracle_scene_struct_size(void) { return (int)sizeof(OracleScene); }
+
+/* ------------------------------------------------------------------------------------------------------
+ * tonemap filters: post_processing_filter.cl:5-51
+ * ------------------------------------------------------------------------------------------------------ */
+/* pow() of the filters as a fixed kernel: log2 / exp2 series in fp64 from + - * / only, rounded once to fp32;
+ * operation for operation the same as dm_powf in chunkyclplugin_b200/csrc/ccu_tonemap.cuh */
+static float dm_powf(float x, float y) {
+    if (x != x || y != y) return NAN;
+    if (x == 0.0f) return 0.0f;
+    if (x == INFINITY || x == -INFINITY) return INFINITY;   /* pow(-inf, y) = +inf for y > 0 that is not an odd integer */
+    if (x < 0.0f) return NAN;
+    double dx = (double)x;
+    int64_t bits;
+    memcpy(&bits, &dx, 8);
+    int e = (int)((bits >> 52) & 0x7FF) - 1023;
+    int64_t mb = (bits & 0x000FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL;
+    double m;
+    memcpy(&m, &mb, 8);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    const double t = (m - 1.0) / (m + 1.0);
+    const double t2 = t * t;
+    double sr = 1.0 / 15.0;
+    sr = sr * t2 + 1.0 / 13.0;
+    sr = sr * t2 + 1.0 / 11.0;
+    sr = sr * t2 + 1.0 / 9.0;
+    sr = sr * t2 + 1.0 / 7.0;
+    sr = sr * t2 + 1.0 / 5.0;
+    sr = sr * t2 + 1.0 / 3.0;
+    sr = sr * t2 + 1.0;
+    const double l2 = (double)e + (t * sr) * 2.8853900817779268;
+    const double p = (double)y * l2;
+    if (p > 200.0) return INFINITY;
+    if (p < -200.0) return 0.0f;
+    const double k = floor(p + 0.5);
+    const double f = (p - k) * 0.6931471805599453;
+    double r = 1.0 / 479001600.0;
+    r = r * f + 1.0 / 39916800.0;
+    r = r * f + 1.0 / 3628800.0;
+    r = r * f + 1.0 / 362880.0;
+    r = r * f + 1.0 / 40320.0;
+    r = r * f + 1.0 / 5040.0;
+    r = r * f + 1.0 / 720.0;
+    r = r * f + 1.0 / 120.0;
+    r = r * f + 1.0 / 24.0;
+    r = r * f + 1.0 / 6.0;
+    r = r * f + 0.5;
+    r = r * f + 1.0;
+    r = r * f + 1.0;
+    int64_t sb = (int64_t)((int)k + 1023) << 52;
+    double scale;
+    memcpy(&scale, &sb, 8);
+    return (float)(r * scale);
+}
+
+static inline uint32_t f2u(float f) {                /* cvt.rzi.u32.f32: saturating, NaN -> 0, toward zero */
+    if (f != f || f <= 0.0f) return 0;
+    if (f >= 4294967296.0f) return UINT32_MAX;
+    return (uint32_t)f;
+}
+
+/* math_mode 1: libm powf instead of the fixed kernel (sensitivity studies) */
+int oracle_tonemap(int width, int height, float exposure, const double *input, int type, int32_t *res, int math_mode, int nthreads) {
+    if (!input || !res || width <= 0 || height <= 0 || type < 0 || type > 3) return -1;
+    const int64_t n = (int64_t)width * height;
+    const float inv_gamma = (float)(1.0 / 2.2);
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t gid = 0; gid < n; gid++) {
+        float c[3];
+        for (int i = 0; i < 3; i++) c[i] = (float)input[gid * 3 + i] * exposure;        /* double.h:19, filter :22 */
+        for (int i = 0; i < 3; i++) {
+            float x = c[i];
+            switch (type) {
+                case 0:
+                    x = math_mode ? powf(x, inv_gamma) : dm_powf(x, inv_gamma);
+                    break;
+                case 1:
+                    x = fmaxf_(0.0f, x - 0.004f);
+                    x = (x * (6.2f * x + 0.5f)) / (x * (6.2f * x + 1.7f) + 0.06f);
+                    break;
+                case 2:
+                    x = (x * (2.51f * x + 0.03f)) / (x * (2.43f * x + 0.59f) + 0.14f);
+                    x = fminf_(fmaxf_(x, 0.0f), 1.0f);
+                    x = math_mode ? powf(x, inv_gamma) : dm_powf(x, inv_gamma);
+                    break;
+                default: {
+                    x = x * 16.0f;
+                    const float a = 0.10f * 0.50f, b = 0.20f * 0.02f, d = 0.20f * 0.30f, g = 0.02f / 0.30f;
+                    x = ((x * (0.15f * x + a) + b) / (x * (0.15f * x + 0.50f) + d)) - g;
+                    const float w = ((11.2f * (0.15f * 11.2f + a) + b) / (11.2f * (0.15f * 11.2f + 0.50f) + d)) - g;
+                    x = x / w;
+                    break;
+                }
+            }
+            c[i] = x;
+        }
+        uint32_t r = f2u(c[0] * 255.0f + 0.5f), g = f2u(c[1] * 255.0f + 0.5f), b = f2u(c[2] * 255.0f + 0.5f);   /* rgba.h:6-16 */
+        if (r > 255u) r = 255u;
+        if (g > 255u) g = 255u;
+        if (b > 255u) b = 255u;
+        res[gid] = (int32_t)((255u << 24) | (r << 16) | (g << 8) | b);
+    }
+    return 0;
+}

@@ -27,6 +27,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_CL = os.path.join(os.path.dirname(_HERE), "_ref", "chunkycl_kernel.cl")
 PROBE_CL = os.path.join(_HERE, "probe_kernels.cl")
+TONEMAP_CL = os.path.join(os.path.dirname(_HERE), "_ref", "chunkycl_tonemap.cl")
 
 CL_DEVICE_TYPE_GPU = 1 << 2
 CL_MEM_READ_WRITE, CL_MEM_READ_ONLY, CL_MEM_COPY_HOST_PTR = 1 << 0, 1 << 2, 1 << 5
@@ -341,3 +342,79 @@ class ClReference:
         for m in self._mem:
             self.cl.clReleaseMemObject(m)
         self._mem = []
+
+
+class ClTonemap:
+    """The reference's tonemap program (tonemap/include/post_processing_filter.cl), built and driven the way
+    GpuPostProcessingFilter.java:35-65 does: upload the double sample buffer, 6 scalar / buffer args, W*H work-items,
+    read the ARGB image back."""
+
+    def __init__(self, strict: bool = False, device_index: int = 0):
+        cl = self.cl = _load()
+        n = C.c_uint32()
+        _chk(cl.clGetPlatformIDs(0, None, C.byref(n)), "clGetPlatformIDs")
+        plats = (C.c_void_p * n.value)()
+        cl.clGetPlatformIDs(n.value, plats, None)
+        nd = C.c_uint32()
+        _chk(cl.clGetDeviceIDs(plats[0], CL_DEVICE_TYPE_GPU, 0, None, C.byref(nd)), "clGetDeviceIDs")
+        devs = (C.c_void_p * nd.value)()
+        cl.clGetDeviceIDs(plats[0], CL_DEVICE_TYPE_GPU, nd.value, devs, None)
+        self.device = C.c_void_p(devs[device_index])
+        err = C.c_int32()
+        dev_arr = (C.c_void_p * 1)(self.device)
+        self.ctx = cl.clCreateContext(None, 1, dev_arr, None, None, C.byref(err))
+        _chk(err.value, "clCreateContext")
+        self.queue = cl.clCreateCommandQueue(self.ctx, self.device, CL_QUEUE_PROFILING_ENABLE, C.byref(err))
+        _chk(err.value, "clCreateCommandQueue")
+        src = open(TONEMAP_CL).read()
+        opts = REFERENCE_BUILD_OPTIONS
+        if strict:
+            src = "#pragma OPENCL FP_CONTRACT OFF\n" + src
+            opts += " -cl-fp32-correctly-rounded-divide-sqrt"
+        sb = src.encode()
+        strs = (C.c_char_p * 1)(sb)
+        lens = (C.c_size_t * 1)(len(sb))
+        self.program = cl.clCreateProgramWithSource(self.ctx, 1, strs, lens, C.byref(err))
+        _chk(err.value, "clCreateProgramWithSource")
+        berr = cl.clBuildProgram(self.program, 1, dev_arr, opts.encode(), None, None)
+        if berr != 0:
+            sz = C.c_size_t()
+            cl.clGetProgramBuildInfo(self.program, self.device, CL_PROGRAM_BUILD_LOG, 0, None, C.byref(sz))
+            buf = C.create_string_buffer(sz.value + 1)
+            cl.clGetProgramBuildInfo(self.program, self.device, CL_PROGRAM_BUILD_LOG, sz.value, buf, None)
+            raise ClError(f"clBuildProgram(tonemap) failed ({berr}):\n{buf.value.decode(errors='replace')}")
+
+    def filter(self, width: int, height: int, exposure: float, sample_buffer: np.ndarray, filter_type: int):
+        cl = self.cl
+        inp = np.ascontiguousarray(sample_buffer, dtype=np.float64).reshape(-1)
+        n = width * height
+        assert inp.size == 3 * n
+        out = np.zeros(n, dtype=np.int32)
+        err = C.c_int32()
+        m_in = C.c_void_p(cl.clCreateBuffer(self.ctx, CL_MEM_READ_ONLY | CL_MEM_COPY_HOST_PTR, inp.nbytes, inp.ctypes.data_as(C.c_void_p), C.byref(err)))
+        _chk(err.value, "clCreateBuffer(input)")
+        m_out = C.c_void_p(cl.clCreateBuffer(self.ctx, CL_MEM_READ_WRITE | CL_MEM_COPY_HOST_PTR, out.nbytes, out.ctypes.data_as(C.c_void_p), C.byref(err)))
+        _chk(err.value, "clCreateBuffer(output)")
+        k = C.c_void_p(cl.clCreateKernel(self.program, b"filter", C.byref(err)))
+        _chk(err.value, "clCreateKernel(filter)")
+        w, h, e, t = C.c_int32(width), C.c_int32(height), C.c_float(exposure), C.c_int32(filter_type)
+        _chk(cl.clSetKernelArg(k, 0, 4, C.byref(w)), "arg0")
+        _chk(cl.clSetKernelArg(k, 1, 4, C.byref(h)), "arg1")
+        _chk(cl.clSetKernelArg(k, 2, 4, C.byref(e)), "arg2")
+        _chk(cl.clSetKernelArg(k, 3, C.sizeof(C.c_void_p), C.byref(m_in)), "arg3")
+        _chk(cl.clSetKernelArg(k, 4, C.sizeof(C.c_void_p), C.byref(m_out)), "arg4")
+        _chk(cl.clSetKernelArg(k, 5, 4, C.byref(t)), "arg5")
+        ev = C.c_void_p()
+        g = (C.c_size_t * 1)(n)
+        _chk(cl.clEnqueueNDRangeKernel(self.queue, k, 1, None, g, None, 0, None, C.byref(ev)), "clEnqueueNDRangeKernel")
+        evs = (C.c_void_p * 1)(ev)
+        _chk(cl.clWaitForEvents(1, evs), "clWaitForEvents")
+        t0, t1 = C.c_uint64(), C.c_uint64()
+        cl.clGetEventProfilingInfo(ev, CL_PROFILING_COMMAND_START, 8, C.byref(t0), None)
+        cl.clGetEventProfilingInfo(ev, CL_PROFILING_COMMAND_END, 8, C.byref(t1), None)
+        cl.clReleaseEvent(ev)
+        _chk(cl.clEnqueueReadBuffer(self.queue, m_out, 1, 0, out.nbytes, out.ctypes.data_as(C.c_void_p), 0, None, None), "clEnqueueReadBuffer")
+        cl.clReleaseKernel(k)
+        cl.clReleaseMemObject(m_in)
+        cl.clReleaseMemObject(m_out)
+        return out, (t1.value - t0.value) * 1e-6
