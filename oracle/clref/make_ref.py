@@ -35,6 +35,16 @@ def main() -> int:
     preprocess(SRC, os.path.join(OUT_DIR, "chunkycl_kernel.cl"))
     if os.path.exists(TONE):
         preprocess(TONE, os.path.join(OUT_DIR, "chunkycl_tonemap.cl"))
+    # the reference's benchmark scene (benchmark/OpenCL_test/), loaded where it lies and packed into the arrays the C ABI
+    # takes: a build output like the .cl files (git-ignored, travels to the GPU box) for scripts/run_render.py --scene benchmark
+    bench = os.path.join(REF, "benchmark", "OpenCL_test")
+    if os.path.exists(os.path.join(bench, "OpenCL_test.octree2")):
+        sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+        import numpy as np
+        from chunkyclplugin_b200 import octree2
+        sc = octree2.load_scene(os.path.join(bench, "OpenCL_test.octree2"), os.path.join(bench, "OpenCL_test.json"), 1920, 1080)
+        np.savez_compressed(os.path.join(OUT_DIR, "benchmark_scene.npz"), octree=sc.octree, octree_depth=sc.octree_depth,
+                            block_palette=sc.block_palette, mat_palette=sc.mat_palette, camera=sc.camera)
     print("wrote", OUT_DIR)
     return 0
 

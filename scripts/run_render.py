@@ -24,6 +24,13 @@ elif a.scene == "entities":
     p = S.entity_scene(256, a.width, a.height)
 elif a.scene == "large":
     p = S.large_world_scene(width=a.width, height=a.height)
+elif a.scene == "benchmark":
+    # the reference's benchmark scene (benchmark/OpenCL_test), packed by oracle/clref/make_ref.py where /root/reference exists
+    import dataclasses
+    z = np.load(os.path.join(ROOT, "oracle", "_ref", "benchmark_scene.npz"))
+    base = S.terrain_scene(8, a.width, a.height)
+    p = dataclasses.replace(base, octree=z["octree"], octree_depth=int(z["octree_depth"]), block_palette=z["block_palette"],
+                            mat_palette=z["mat_palette"], camera=z["camera"], name="benchmark")
 else:
     raise SystemExit("unknown scene")
 ctx = native.Context(0)
