@@ -14,12 +14,13 @@
 //           column right away, so the march loop keeps (close to) 32 busy lanes; when too few lanes are busy and
 //           another stage has more work the warp parks its rays (t / steps written back) and switches;
 //   BLOCK   block / material test of the non-air leaf the ray reached (block.h:30-118); miss -> MARCH;
-//           hit -> BVHs, then surface response + sun sampling (kernel.h:33-44, sky.h:68-93) -> MARCH (shadow ray),
-//           or BOUNCE when the ray was the shadow ray;
-//   EXIT    the ray left the octree: BVHs, sky + sun disc (kernel.h:26-31) -> BOUNCE (shadow ray) or END;
-//   BOUNCE  diffuse bounce (kernel.h:46-98) -> MARCH, or END at the depth limit;
+//           hit -> surface response + sun sampling (kernel.h:33-44, sky.h:68-93) -> MARCH (shadow ray); when the ray
+//           was the shadow ray the diffuse bounce (kernel.h:46-98) follows right away -> MARCH, or END at the depth limit;
+//   EXIT    the ray left the octree: sky + sun disc (kernel.h:26-31), then the bounce (shadow ray) -> MARCH, or END;
 //   END     fold the sample into the running mean (rayTracer.cl:109-112), next pass or next pixel (global work
-//           counter), camera ray (rayTracer.cl:55-91) -> MARCH.
+//           counter), camera ray (rayTracer.cl:55-91) -> MARCH;
+//   BVH, SHADE   only in the kernels for scenes with entity BVHs: BLOCK / EXIT hand the ray to the BVH stage
+//           (bvh.h:22-113, world then actor BVH), SHADE then does the shading BLOCK / EXIT do directly otherwise.
 //
 // Scheduling does not touch arithmetic: every path performs exactly the operations of the thread-per-pixel
 // kernel in the same order (RNG draw order, per-pixel pass order), so the image is bit-identical.
@@ -44,7 +45,7 @@ static_assert(Q_ROWS >= 1 && Q_ROWS <= 64, "at most two mask words per stage and
 // QS_BVH / QS_SHADE exist only in the kernels built for scenes with entity BVHs (HAS_BVH): there the BVH traversal runs as
 // a stage of its own between the octree part of closestIntersect (BLOCK / EXIT) and the shading (SHADE); without BVHs
 // BLOCK / EXIT shade directly.
-enum QStage : int { QS_MARCH = 0, QS_BLOCK, QS_EXIT, QS_BOUNCE, QS_END, QS_BVH, QS_SHADE, QS_COUNT_BVH };
+enum QStage : int { QS_MARCH = 0, QS_BLOCK, QS_EXIT, QS_END, QS_BVH, QS_SHADE, QS_COUNT_BVH };
 constexpr int QS_COUNT = QS_BVH;   // stages of the kernels without BVHs
 
 // Slot fields.  The running mean stays in the accumulation buffer (read-modify-write per sample, L2 only); the
@@ -275,13 +276,17 @@ __device__ __forceinline__ void q_stage_march(const DScene &s, const unsigned *_
     }
 }
 
-// What follows closestIntersect in rayTracer.cl:93-106 for a ray whose closest hit is known: sky for a miss
-// (kernel.h:26-31), otherwise the surface response (kernel.h:33-44) and the sun sampling ray (sky.h:68-93).
+// What follows closestIntersect in rayTracer.cl:93-107 for a ray whose closest hit is known: sky for a miss
+// (kernel.h:26-31), otherwise the surface response (kernel.h:33-44) and the sun sampling ray (sky.h:68-93); when the ray
+// was the shadow ray (or sun sampling is off) the diffuse bounce (nextPath, kernel.h:46-98) follows right away.
 __device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *mask, int lane, int row, float3 o, float3 d, float distance,
                                         bool ray_hit, const Surf &hit) {
     const int slot = row * 32 + lane;
-    const uint32_t meta = QU(QF_META) & ~QM_HIT;
+    uint32_t meta = QU(QF_META) & ~QM_HIT;
     const bool shadow = (meta & QM_SHADOW) != 0;
+    bool bounce = false;
+    float3 bounce_from = o;          // the shadow ray starts at the surface point
+    float3 bounce_normal = f3(0, 0, 0);
     if (!ray_hit) {
         // kernel.h:26-31 with emittance 1 (path segment) or |d.n| (shadow ray)
         float3 throughput = f3(QFL(QF_THRX), QFL(QF_THRY), QFL(QF_THRZ));
@@ -289,9 +294,10 @@ __device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *
         float3 sky = sky_radiance(s, d);
         color = color + (sky * throughput) * (shadow ? QFL(QF_SHW) : 1.0f);
         QFL(QF_COLX) = color.x; QFL(QF_COLY) = color.y; QFL(QF_COLZ) = color.z;
-        q_push(mask, shadow ? QS_BOUNCE : QS_END, lane, row);
+        if (shadow) bounce = true;
+        else q_push(mask, QS_END, lane, row);
     } else if (shadow) {
-        q_push(mask, QS_BOUNCE, lane, row);
+        bounce = true;
     } else {
         // kernel.h:20-22 + applyRayColor kernel.h:33-44
         float3 throughput = f3(QFL(QF_THRX), QFL(QF_THRY), QFL(QF_THRZ));
@@ -302,8 +308,8 @@ __device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *
         color = color + (col * (hit.emittance * s.emitter_scale)) * throughput;
         QFL(QF_THRX) = throughput.x; QFL(QF_THRY) = throughput.y; QFL(QF_THRZ) = throughput.z;
         QFL(QF_COLX) = color.x; QFL(QF_COLY) = color.y; QFL(QF_COLZ) = color.z;
-        QFL(QF_SNX) = hit.normal.x; QFL(QF_SNY) = hit.normal.y; QFL(QF_SNZ) = hit.normal.z;
         if (s.sun_flags & 1) {
+            QFL(QF_SNX) = hit.normal.x; QFL(QF_SNY) = hit.normal.y; QFL(QF_SNZ) = hit.normal.z;
             uint32_t rng = QU(QF_RNG);
             float x1 = rng_float(rng);
             float x2 = rng_float(rng);
@@ -316,8 +322,29 @@ __device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *
             const bool entered = march_begin(s, m, surf_point, sd, distance);
             q_store_ray(F, mask, lane, row, m, entered);
         } else {
-            QFL(QF_OX) = surf_point.x; QFL(QF_OY) = surf_point.y; QFL(QF_OZ) = surf_point.z;
-            q_push(mask, QS_BOUNCE, lane, row);
+            bounce = true;
+            bounce_from = surf_point;
+            bounce_normal = hit.normal;
+        }
+    }
+    if (bounce) {
+        // nextPath, kernel.h:46-98
+        if (shadow) bounce_normal = f3(QFL(QF_SNX), QFL(QF_SNY), QFL(QF_SNZ));
+        uint32_t rng = QU(QF_RNG);
+        float x1 = rng_float(rng);
+        float x2 = rng_float(rng);
+        QU(QF_RNG) = rng;
+        float3 nd = diffuse_direction(bounce_normal, x1, x2);
+        float3 no = bounce_from + nd * CCU_OFFSET;
+        const int ray_depth = (int)((meta >> 16) & 0xFF) + 1;
+        meta = (meta & ~(0xFFu << 16) & ~QM_SHADOW) | ((uint32_t)ray_depth << 16);
+        QU(QF_META) = meta;
+        if (ray_depth < s.max_depth) {
+            March m;
+            const bool entered = march_begin(s, m, no, nd, inff_());
+            q_store_ray(F, mask, lane, row, m, entered);
+        } else {
+            q_push(mask, QS_END, lane, row);
         }
     }
 }
@@ -547,32 +574,6 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
     }
 }
 
-// kernel.h:46-98.  QF_O* holds the surface point (the origin of the shadow ray, or written by the resolve stage).
-__device__ __forceinline__ void q_stage_bounce(const DScene &s, uint32_t *F, unsigned *mask, int lane) {
-    const int row = q_pop(mask, QS_BOUNCE, lane);
-    QSTAT(2 * QS_BOUNCE, 1); QSTAT(2 * QS_BOUNCE + 1, __popc(__ballot_sync(0xffffffffu, row >= 0)));
-    if (row < 0) return;
-    const int slot = row * 32 + lane;
-    uint32_t rng = QU(QF_RNG);
-    float x1 = rng_float(rng);
-    float x2 = rng_float(rng);
-    QU(QF_RNG) = rng;
-    float3 n = f3(QFL(QF_SNX), QFL(QF_SNY), QFL(QF_SNZ));
-    float3 d = diffuse_direction(n, x1, x2);
-    float3 o = f3(QFL(QF_OX), QFL(QF_OY), QFL(QF_OZ)) + d * CCU_OFFSET;
-    uint32_t meta = QU(QF_META);
-    int ray_depth = (int)((meta >> 16) & 0xFF) + 1;
-    meta = (meta & ~(0xFFu << 16) & ~QM_SHADOW) | ((uint32_t)ray_depth << 16);
-    QU(QF_META) = meta;
-    if (ray_depth < s.max_depth) {
-        March m;
-        const bool entered = march_begin(s, m, o, d, inff_());
-        q_store_ray(F, mask, lane, row, m, entered);
-    } else {
-        q_push(mask, QS_END, lane, row);
-    }
-}
-
 constexpr int Q_TILE_W = 32, Q_TILE_H = 32;
 constexpr unsigned Q_CHUNK = Q_TILE_W * Q_TILE_H;
 // k-th pixel in tile order (bands of Q_TILE_H rows, each cut into tiles Q_TILE_W wide, row-major inside a tile;
@@ -739,7 +740,6 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
             case QS_MARCH: QSTAT(0, 1); q_stage_march<NST>(s, top, F, mask, lane, qp.yield_below, qp.refill_min); break;
             case QS_BLOCK:
             case QS_EXIT: q_stage_resolve<HAS_BVH>(s, F, mask, lane, best == QS_BLOCK); break;
-            case QS_BOUNCE: q_stage_bounce(s, F, mask, lane); break;
             case QS_END: q_stage_end(s, qp.w, F, mask, live, lane); break;
             case QS_BVH: QSTAT(16, 1); if (HAS_BVH) q_stage_bvh(s, F, mask, lane, qp.refill_min, qp.leaf_min); break;
             default: if (HAS_BVH) q_stage_shade(s, F, mask, lane); break;

@@ -280,11 +280,11 @@ struct ccu_ctx {
     int wait_lanes = 28;
     int refill_min = 4;
     int exit_idle = 8;
-    int yield_below = 16;
+    int yield_below = 20;
     int q_refill_min = 8;
     int q_march_bias = 4;
     int q_leaf_min = 12;
-    int q_bvh_warps = 24;
+    int q_bvh_warps = 23;
     int q_march_warps = 22;
     int blocks_per_sm = CCU_MIN_BLOCKS;
     int seeds_cap = 0;
@@ -1022,7 +1022,7 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
             qp.march_bias = c->q_march_bias;
             qp.leaf_min = c->q_leaf_min;
             qp.bvh_warps = c->q_bvh_warps;
-            qp.march_warps = c->q_march_warps;
+            qp.march_warps = bvh ? 64 : c->q_march_warps;   // with BVHs the service warps are the ones that do not walk
             const bool tops = c->air_top.n <= (size_t)Q_TOP_WORDS && getenv("CCU_NO_TOPS") == nullptr;
             const int grid = c->sm_count, block = Q_WARPS * 32;
             if (!c->use_air) return fail(CCU_ESTATE, "ccu_render_passes: kernel 4 needs the air layout (malformed octree?)");
@@ -1039,9 +1039,9 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
                 cudaStreamSynchronize(c->stream);
                 unsigned long long st[32];
                 cudaMemcpyFromSymbol(st, g_qstats, sizeof st);
-                const char *names[5] = {"march", "block", "exit", "bounce", "end"};
+                const char *names[4] = {"march", "block", "exit", "end"};
                 fprintf(stderr, "[qstats] ");
-                for (int i = 1; i < 5; i++) fprintf(stderr, "%s: %llu x %.1f lanes  ", names[i], st[2 * i], st[2 * i] ? (double)st[2 * i + 1] / st[2 * i] : 0.0);
+                for (int i = 1; i < 4; i++) fprintf(stderr, "%s: %llu x %.1f lanes  ", names[i], st[2 * i], st[2 * i] ? (double)st[2 * i + 1] / st[2 * i] : 0.0);
                 fprintf(stderr, "\n[qstats] march stages %llu, iterations %llu x %.1f lanes in flight, yields %llu, idle rounds %llu, pops %llu retries %llu\n", st[0], st[10],
                         st[10] ? (double)st[11] / st[10] : 0.0, st[13], st[12], st[14], st[15]);
                 fprintf(stderr, "[qstats] bvh stages %llu, steps %llu x %.1f walking lanes, leaf turns %llu x %.1f lanes, shade %llu x %.1f lanes\n", st[16], st[18],

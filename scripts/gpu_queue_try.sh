@@ -1,6 +1,2 @@
 #!/bin/bash
-make -C oracle CC=gcc >/dev/null
-timeout 500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-echo -n "benchmark scene (reference's Greenfield fixture) 1080p kernel4: "; timeout 300 python scripts/run_render.py --scene benchmark --passes 8 --windows 2 --kernel 4 | grep "window 1"
-echo -n "benchmark scene kernel3: "; timeout 300 python scripts/run_render.py --scene benchmark --passes 8 --windows 2 --kernel 3 | grep "window 1"
-echo -n "benchmark scene kernel1: "; timeout 300 python scripts/run_render.py --scene benchmark --passes 8 --windows 2 --kernel 1 | grep "window 1"
+for b in 20 22 23 24 25; do for m in 22 28; do echo -n "entities bvh_warps=$b march_warps=$m: "; CCU_Q_BVH_WARPS=$b CCU_Q_MARCH_WARPS=$m timeout 300 python scripts/run_render.py --scene entities --passes 4 --windows 2 --kernel 4 | grep "window 1"; done; done
