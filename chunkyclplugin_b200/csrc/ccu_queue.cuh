@@ -39,7 +39,10 @@ namespace ccu {
 constexpr int Q_WARPS = CCU_Q_WARPS;       // warps per CTA (one CTA per SM)
 constexpr int Q_ROWS = CCU_Q_ROWS;         // slots per lane column
 constexpr int Q_SLOTS = Q_ROWS * 32;
-constexpr int Q_MW = (Q_ROWS + 31) / 32;   // mask words per stage and column
+constexpr int Q_MW = (Q_ROWS + 31) / 32;   // 32-bit words per work mask (one mask per stage and column; 64-bit masks for > 32 rows)
+template <int MW> struct QMaskType { typedef unsigned type; };
+template <> struct QMaskType<2> { typedef unsigned long long type; };
+typedef QMaskType<Q_MW>::type qmask_t;
 static_assert(Q_ROWS >= 1 && Q_ROWS <= 64, "at most two mask words per stage and column");
 
 // QS_BVH / QS_SHADE exist only in the kernels built for scenes with entity BVHs (HAS_BVH): there the BVH traversal runs as
@@ -157,40 +160,33 @@ __device__ __forceinline__ int lean_probe(const DScene &s, const unsigned *__res
 }
 
 // ------------------------------------------------------------------------------------------------------
-// work masks: mask[(stage * Q_MW + word) * 32 + column], bit = row within the word
+// work masks: one qmask_t per stage and column, word index stage * 32 + column, bit = row
 // ------------------------------------------------------------------------------------------------------
 // Lowest set bit first: warps that pop the same stage at the same time contend for the same rows, and the winner
 // takes (most of) a row across all columns.  Rows therefore tend to stay together from stage to stage, which keeps
 // the batches full; spreading the warps over different rows (measured) fragments the batches and is slower.
-__device__ __forceinline__ int q_pop_word(unsigned *word) {
-    unsigned m = *reinterpret_cast<volatile unsigned *>(word);
+__device__ __forceinline__ int q_pop(unsigned *mask, int stage, int lane) {
+    qmask_t *word = reinterpret_cast<qmask_t *>(mask) + stage * 32 + lane;
+    qmask_t m = *reinterpret_cast<volatile qmask_t *>(word);
     while (m) {
-        const unsigned bit = m & (0u - m);
-        const unsigned old = atomicAnd(word, ~bit);
+        const qmask_t bit = m & (qmask_t(0) - m);
+        const qmask_t old = atomicAnd(word, ~bit);
         QSTAT_LANE(14, 1);
-        if (old & bit) return __ffs((int)bit) - 1;
+        if (old & bit) {
+            __threadfence_block();
+            return (Q_MW > 1 ? __ffsll((long long)bit) : __ffs((int)bit)) - 1;
+        }
         QSTAT_LANE(15, 1);
         m = old & ~bit;
     }
     return -1;
 }
-__device__ __forceinline__ int q_pop(unsigned *mask, int stage, int lane) {
-    int row = q_pop_word(mask + (stage * Q_MW) * 32 + lane);
-    if (Q_MW > 1 && row < 0) {
-        row = q_pop_word(mask + (stage * Q_MW + 1) * 32 + lane);
-        if (row >= 0) row += 32;
-    }
-    if (row >= 0) __threadfence_block();
-    return row;
-}
 __device__ __forceinline__ void q_push(unsigned *mask, int stage, int lane, int row) {
     __threadfence_block();
-    atomicOr(mask + (stage * Q_MW + (Q_MW > 1 ? (row >> 5) : 0)) * 32 + lane, 1u << (row & 31));
+    atomicOr(reinterpret_cast<qmask_t *>(mask) + stage * 32 + lane, qmask_t(1) << row);
 }
 __device__ __forceinline__ bool q_has_work(const unsigned *mask, int stage, int lane) {
-    unsigned m = *reinterpret_cast<const volatile unsigned *>(mask + (stage * Q_MW) * 32 + lane);
-    if (Q_MW > 1) m |= *reinterpret_cast<const volatile unsigned *>(mask + (stage * Q_MW + 1) * 32 + lane);
-    return m != 0;
+    return *(reinterpret_cast<const volatile qmask_t *>(mask) + stage * 32 + lane) != 0;
 }
 
 #define QI(f) (*reinterpret_cast<int *>(&F[(f) * Q_SLOTS + slot]))
@@ -697,11 +693,8 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
     const int lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < Q_SLOTS; i += blockDim.x) F[QF_META * Q_SLOTS + i] = QM_NEEDPIX;
-    for (int i = threadIdx.x; i < MASK_WORDS; i += blockDim.x) {
-        const int st = i / (Q_MW * 32), word = (i / 32) % Q_MW;
-        const int rows = min(32, Q_ROWS - 32 * word);
-        mask[i] = st == QS_END ? (rows == 32 ? 0xffffffffu : ((1u << rows) - 1u)) : 0u;
-    }
+    for (int i = threadIdx.x; i < NST * 32; i += blockDim.x)
+        reinterpret_cast<qmask_t *>(mask)[i] = (i / 32 == QS_END) ? (Q_ROWS == 8 * (int)sizeof(qmask_t) ? ~qmask_t(0) : ((qmask_t(1) << Q_ROWS) - 1)) : qmask_t(0);
     if (TOPS) {
         const int n = 1 << (3 * s.top_log2);
         for (int i = threadIdx.x; i < n; i += blockDim.x) top_s[i] = __ldg(s.air_top + i);

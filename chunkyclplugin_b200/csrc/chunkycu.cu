@@ -578,6 +578,7 @@ int bvh_ref(const std::vector<int> &bvh, const std::vector<int> &trigs, size_t n
 WideLayout build_wide_layout(const int *tree, size_t n, int depth) {
     WideLayout b;
     int cl = std::max(depth - 7, 4);
+    if (const char *e = getenv("CCU_CELL_LEVEL")) cl = std::max(0, atoi(e));   // tuning knob: level of the top table's cells
     if (cl & 1) cl++;
     if (cl > depth) cl = depth & ~1;
     b.cell_level = cl;

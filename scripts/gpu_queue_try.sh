@@ -1,2 +1,2 @@
 #!/bin/bash
-for b in 20 22 23 24 25; do for m in 22 28; do echo -n "entities bvh_warps=$b march_warps=$m: "; CCU_Q_BVH_WARPS=$b CCU_Q_MARCH_WARPS=$m timeout 300 python scripts/run_render.py --scene entities --passes 4 --windows 2 --kernel 4 | grep "window 1"; done; done
+for cl in 4 6 8; do echo -n "large 4K cell_level=$cl: "; CCU_CELL_LEVEL=$cl timeout 600 python scripts/run_render.py --scene large --width 3840 --height 2160 --passes 4 --windows 2 --kernel 4 | grep "window 1"; done
