@@ -1,2 +1,6 @@
 #!/bin/bash
-for cl in 4 6 8; do echo -n "large 4K cell_level=$cl: "; CCU_CELL_LEVEL=$cl timeout 600 python scripts/run_render.py --scene large --width 3840 --height 2160 --passes 4 --windows 2 --kernel 4 | grep "window 1"; done
+make -C oracle CC=gcc >/dev/null
+RS="8" YS="16 20 24" bash scripts/sweep_queue2.sh "-DCCU_Q_PARTNER"
+CCU_NVCC_EXTRA="-DCCU_Q_PARTNER" python chunkyclplugin_b200/build.py --force >/dev/null
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "queue" 2>&1 | tail -3
+python chunkyclplugin_b200/build.py --force >/dev/null
