@@ -295,10 +295,14 @@ def main():
         ctx.render_end()
         renderer = CudaPathTracingRenderer(loader)
         e_samples, e_secs = 0, 0.0
+        # one Chunky scene object for all steps, as in Chunky (the double sample buffer is allocated once per scene and
+        # stays resident); every step is a fresh render of SPP_PER_STEP passes into it
+        cs = Scene(scene, target_spp=SPP_PER_STEP)
+        cs.packed = scene                                  # same scene object: no re-upload
+        mgr = DefaultRenderManager(cs)
         for i in range(3 + max(3, args.steps // 2)):
-            cs = Scene(scene, target_spp=SPP_PER_STEP)
-            cs.packed = scene                              # same scene object: no re-upload
-            mgr = DefaultRenderManager(cs)
+            cs.spp = 0
+            cs.sample_buffer.fill(0.0)
             flush.fill_(i)
             torch.cuda.synchronize()
             if world > 1:

@@ -241,6 +241,7 @@ struct ccu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // read-back chunks of ccu_render_merge
     std::mutex mu;
     int sm_count = 0;
 
@@ -705,6 +706,7 @@ int ccu_ctx_destroy(ccu_ctx *c) {
         if (c->seeds_dev) cudaFree(c->seeds_dev);
         if (c->work_counter) cudaFree(c->work_counter);
         if (c->unorm) cudaFree(c->unorm);
+        for (auto &e : c->chunk_ev) if (e) cudaEventDestroy(e);
         cudaEventDestroy(c->ev0);
         cudaEventDestroy(c->ev1);
         cudaStreamDestroy(c->stream);
@@ -1113,30 +1115,53 @@ int ccu_render_merge(ccu_ctx *c, double *sample_buffer, int32_t sample_spp, int3
     std::lock_guard<std::mutex> lk(c->mu);
     if (!c->accum || !c->target_live) return fail(CCU_ESTATE, "ccu_render_merge: no render target");
     DeviceGuard g(c->device);
-    int rc = fetch_mean(c);
-    if (rc != CCU_OK) return rc;
     int pass_spp = c->window_spp;
     if (merged_spp) *merged_spp = pass_spp;
-    if (pass_spp == 0) return CCU_OK;
-    // OpenClPathTracingRenderer.java:167-173
+    if (pass_spp == 0) {
+        CU(cudaStreamSynchronize(c->stream));
+        stop_timer(c);
+        return CCU_OK;
+    }
+    // OpenClPathTracingRenderer.java:164-173: blocking read of the float buffer, then the spp-weighted merge on the host.
+    // The read-back is cut into chunks so that the merge of chunk k overlaps the copy of chunk k+1.
     const double sinv = 1.0 / (double)(sample_spp + pass_spp);
     const double ds = (double)sample_spp, dp = (double)pass_spp;
-    size_t n = (size_t)c->width * c->height * 3;
+    const size_t n = (size_t)c->width * c->height * 3;
+    constexpr int NCH = 8;
+    if (!c->chunk_ev[0]) {
+        for (int k = 0; k < NCH; k++) CU(cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming));
+    }
+    const size_t chunk = ((n + NCH - 1) / NCH + 63) & ~(size_t)63;
+    for (int k = 0; k < NCH; k++) {
+        const size_t lo = std::min(n, k * chunk), hi = std::min(n, (k + 1) * chunk);
+        if (hi > lo) CU(cudaMemcpyAsync(c->pinned + lo, c->accum + lo, (hi - lo) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(c->chunk_ev[k], c->stream));
+    }
     unsigned hw = std::thread::hardware_concurrency();
     unsigned nt = std::max(1u, std::min(16u, hw ? hw : 4u));
     if (n < (1u << 20)) nt = 1;
     const float *src = c->pinned;
-    auto work = [=](size_t lo, size_t hi) {
-        for (size_t i = lo; i < hi; i++) sample_buffer[i] = (sample_buffer[i] * ds + (double)src[i] * dp) * sinv;
+    cudaEvent_t *evs = c->chunk_ev;
+    const int device = c->device;
+    auto work = [=](unsigned t) {
+        cudaSetDevice(device);
+        for (int k = 0; k < NCH; k++) {
+            const size_t lo = std::min(n, k * chunk), hi = std::min(n, (k + 1) * chunk);
+            cudaEventSynchronize(evs[k]);
+            const size_t len = hi - lo, part = (len + nt - 1) / nt;
+            const size_t a = lo + std::min(len, t * part), b = lo + std::min(len, (t + 1) * part);
+            for (size_t i = a; i < b; i++) sample_buffer[i] = (sample_buffer[i] * ds + (double)src[i] * dp) * sinv;
+        }
     };
     if (nt == 1) {
-        work(0, n);
+        work(0);
     } else {
         std::vector<std::thread> th;
-        size_t chunk = (n + nt - 1) / nt;
-        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, std::min(n, t * chunk), std::min(n, (t + 1) * chunk));
+        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
         for (auto &t : th) t.join();
     }
+    CU(cudaStreamSynchronize(c->stream));
+    stop_timer(c);
     c->window_spp = 0;   // bufferSppReal = 0 (:170)
     return CCU_OK;
 }
