@@ -79,8 +79,9 @@ struct Record {      // IntersectionRecord, wavefront.h:37-78
 };
 
 struct HitInfo {     // first-hit bookkeeping, not part of the reference's record
-    int node;
-    int kind;
+    int node;        // treeData index of the hit leaf (reference layout), -1 when unknown / BVH hit
+    int kind;        // 0 miss, 1 octree, 2 world BVH, 3 actor BVH
+    int bx, by, bz;  // voxel of the octree hit
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -485,13 +486,15 @@ __device__ __forceinline__ bool march_block(const DScene &s, March &m, int data,
 
 // One whole iteration.  Returns 0 = keep marching, 1 = hit (hit_t / surf / block / node filled), 2 = ray left.
 template <bool WIDE>
-__device__ __forceinline__ int march_step(const DScene &s, March &m, Surf &surf, float &hit_t, int &hit_block, int &hit_node) {
+__device__ __forceinline__ int march_step(const DScene &s, March &m, Surf &surf, float &hit_t, int &hit_block, int &hit_node, Cell &hit_cell) {
     int data, level, node;
     int r = march_probe<WIDE>(s, m, data, level, node);
     if (r != 1) return r;
+    const Cell c = march_cell(m);
     if (march_block(s, m, data, level, surf, hit_t)) {
         hit_block = data;
         hit_node = node;
+        hit_cell = c;
         return 1;
     }
     return 0;
@@ -504,12 +507,14 @@ __device__ __forceinline__ bool octree_intersect(const DScene &s, float3 origin,
     for (;;) {
         float t;
         int block, node;
-        int r = march_step<WIDE>(s, m, rec.surf, t, block, node);
+        Cell cell;
+        int r = march_step<WIDE>(s, m, rec.surf, t, block, node, cell);
         if (r == 1) {
             rec.distance = t;
             rec.material = block;
             hi.node = node;
             hi.kind = 1;
+            hi.bx = cell.bx; hi.by = cell.by; hi.bz = cell.bz;
             return true;
         }
         if (r == 2) return false;
@@ -730,7 +735,7 @@ __device__ __forceinline__ float3 sample_pixel(const DScene &s, int gid, int see
     rec.surf.normal = f3(0, 0, 0);
     rec.surf.color = make_float4(0, 0, 0, 0);
     rec.surf.emittance = 0;
-    HitInfo hi = {-1, 0};
+    HitInfo hi = {-1, 0, 0, 0, 0};
     for (;;) {
         if (!closest_intersect<WIDE>(s, origin, direction, rec, hi)) {
             // miss: emittance = 1, sky (+ sun disc) added through the throughput (rayTracer.cl:95-97, kernel.h:26-31)

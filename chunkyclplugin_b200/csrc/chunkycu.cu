@@ -71,6 +71,9 @@ __device__ __forceinline__ int face_of(float3 n) {
     return 6;
 }
 
+// WIDE: march on the commit-time layout; the treeData index of the hit leaf (reference numbering, ClSceneLoader.java:56-59)
+// is then found by one root descent for the hit voxel only.
+template <bool WIDE>
 __global__ void __launch_bounds__(128) k_first_hit(const __grid_constant__ DScene s, int seed, int n_pixels, int *block, int *face, int *node,
                                                    int *kind, float *t, float *normal, float *color) {
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,8 +85,12 @@ __global__ void __launch_bounds__(128) k_first_hit(const __grid_constant__ DScen
     Record rec;
     rec.distance = inff_(); rec.material = 0; rec.surf.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
     rec.surf.color = make_float4(0, 0, 0, 0); rec.surf.emittance = 0;
-    HitInfo hi = {-1, 0};
-    bool hit = closest_intersect<false>(s, o, d, rec, hi);   // reference layout: reports the leaf's treeData index
+    HitInfo hi = {-1, 0, 0, 0, 0};
+    bool hit = closest_intersect<WIDE>(s, o, d, rec, hi);
+    if (WIDE && hit && hi.kind == 1) {
+        int level;
+        find_leaf(s, hi.bx, hi.by, hi.bz, level, hi.node);
+    }
     if (block) block[gid] = hit ? rec.material : 0;
     if (face) face[gid] = hit ? face_of(rec.surf.normal) : 6;
     if (node) node[gid] = hit ? hi.node : -1;
@@ -101,6 +108,7 @@ __global__ void __launch_bounds__(128) k_first_hit(const __grid_constant__ DScen
 }
 
 // rayTracer.cl:141-216
+template <bool WIDE>
 __global__ void __launch_bounds__(128) k_preview(const __grid_constant__ DScene s, int n_pixels, int *res) {
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_pixels) return;
@@ -117,9 +125,9 @@ __global__ void __launch_bounds__(128) k_preview(const __grid_constant__ DScene 
     Record rec;
     rec.distance = inff_(); rec.material = 0; rec.surf.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
     rec.surf.color = make_float4(0, 0, 0, 0); rec.surf.emittance = 0;
-    HitInfo hi = {-1, 0};
+    HitInfo hi = {-1, 0, 0, 0, 0};
     float3 c;
-    if (closest_intersect<false>(s, o, d, rec, hi)) {
+    if (WIDE ? closest_intersect<true>(s, o, d, rec, hi) : closest_intersect<false>(s, o, d, rec, hi)) {
         float shading = dot3(rec.surf.normal, f3(0.25f, 0.866f, 0.433f));
         shading = fmaxf(0.3f, shading);
         c = f3(rec.surf.color.x * shading, rec.surf.color.y * shading, rec.surf.color.z * shading);
@@ -1219,7 +1227,8 @@ int ccu_first_hit(ccu_ctx *c, int32_t seed, int32_t *block, int32_t *face, int32
     float *d_normal = reinterpret_cast<float *>(scratch + 9 * n);
     fill_scene(c);
     cudaEventRecord(c->ev0, c->stream);
-    k_first_hit<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color);
+    if (c->scene.use_wide) k_first_hit<true><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color);
+    else k_first_hit<false><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color);
     c->launches++;
     cudaEventRecord(c->ev1, c->stream);
     c->timing_pending = true;
@@ -1248,7 +1257,8 @@ int ccu_preview(ccu_ctx *c, int32_t *argb) {
     CU(cudaMalloc(&d, n * sizeof(int)));
     fill_scene(c);
     cudaEventRecord(c->ev0, c->stream);
-    k_preview<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, (int)n, d);
+    if (c->scene.use_wide) k_preview<true><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, (int)n, d);
+    else k_preview<false><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, (int)n, d);
     c->launches++;
     cudaEventRecord(c->ev1, c->stream);
     c->timing_pending = true;
