@@ -206,3 +206,63 @@ def test_reference_layout_descent_equals_wide_layout(scenes):
         finally:
             c.close()
     assert np.array_equal(_bits(imgs[0]), _bits(imgs[1]))
+
+
+def test_two_contexts_render_concurrently_from_two_threads(scenes):
+    """Every export is thread-safe per context (SURVEY 8b threading row): two host threads, one context each, at once."""
+    import threading
+    import oracle
+    from chunkyclplugin_b200 import native
+    names = ["terrain64", "indoor"]
+    seeds = pass_seeds(5)
+    out, errs = {}, []
+
+    def worker(name):
+        try:
+            ctx = native.Context(0)
+            p = scenes(name)
+            for _ in range(3):
+                load_scene(ctx, p)
+                ctx.render_passes(seeds)
+                out[name], _ = ctx.render_read()
+            ctx.close()
+        except Exception as e:      # surfaced in the main thread
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(n,)) for n in names]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for n in names:
+        assert np.array_equal(_bits(out[n]), _bits(oracle.Oracle(scenes(n)).render(seeds))), n
+
+
+def test_one_context_shared_by_threads(scenes, cuda_ctx):
+    """The camera upload / preview path may be called from another thread than the pass loop (renderLock in the
+    reference, OpenClPathTracingRenderer.java:56,103,142): calls serialise on the context's mutex."""
+    import threading
+    import oracle
+    p = scenes("terrain64")
+    load_scene(cuda_ctx, p)
+    seeds = pass_seeds(8)
+    stop = threading.Event()
+    errs = []
+
+    def camera_thread():
+        try:
+            while not stop.is_set():
+                cuda_ctx.camera_set(p.projector_type, p.camera)
+        except Exception as e:
+            errs.append(e)
+
+    t = threading.Thread(target=camera_thread)
+    t.start()
+    try:
+        for i in range(0, 8, 2):
+            cuda_ctx.render_passes(seeds[i:i + 2])
+    finally:
+        stop.set()
+        t.join()
+    assert not errs, errs
+    got, spp = cuda_ctx.render_read()
+    assert spp == 8 and np.array_equal(_bits(got), _bits(oracle.Oracle(p).render(seeds)))
