@@ -67,6 +67,20 @@ def test_render_depth11_world(scenes, cuda_ctx):
     assert got.max() > 0
 
 
+@pytest.mark.parametrize("wh", [(75, 41), (33, 70), (1, 1), (31, 5)])
+def test_render_odd_canvas_sizes(wh, cuda_ctx):
+    """Canvas sizes that are not multiples of the 32x32 pixel tiles the default kernel hands pixels out in."""
+    import dataclasses
+    import oracle
+    from chunkyclplugin_b200 import scenes as S
+    p = dataclasses.replace(S.terrain_scene(64, 160, 90, seed=7), width=wh[0], height=wh[1])
+    load_scene(cuda_ctx, p)
+    seeds = pass_seeds(3)
+    cuda_ctx.render_passes(seeds)
+    got, _ = cuda_ctx.render_read()
+    assert np.array_equal(_bits(got), _bits(oracle.Oracle(p).render(seeds)))
+
+
 def test_render_top_table_in_global_memory(scenes, cuda_ctx, monkeypatch):
     """The default kernel with its shared-memory staging of the top table switched off gives the same image."""
     import oracle
