@@ -308,7 +308,18 @@ def main():
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            renderer.render(mgr)                           # render_begin, 16 passes, merge into the double buffer, render_end
+            if world == 1:
+                renderer.render(mgr)                       # render_begin, 16 passes, merge into the double buffer, render_end
+            else:
+                # N GPUs: every rank renders its 16 passes of the 16*N-pass window, one NCCL reduce, rank 0 alone merges the
+                # window into the host sample buffer (what a multi-GPU plugin host does; the other ranks hold no host buffer)
+                ctx.camera_set(scene.projector_type, scene.camera)
+                ctx.render_begin(WIDTH, HEIGHT)
+                spr.render_and_merge(step_seeds(), cs.sample_buffer if rank == 0 else None, 0)
+                ctx.render_end()
+                cs.spp = SPP_PER_STEP
+                if rank != 0:
+                    cs.sample_buffer[0] = 1.0
             dt = time.perf_counter() - t0
             if i >= 3:
                 e_samples += WIDTH * HEIGHT * SPP_PER_STEP
@@ -319,7 +330,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": e_samples * world / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": 4 * SPP_PER_STEP,
                "d2h_bytes_per_step": 4 * 3 * WIDTH * HEIGHT,
-               "how": "CudaPathTracingRenderer.render(): render_begin + 16 passes + ccu_render_merge into the host double buffer"}
+               "how": "CudaPathTracingRenderer.render(): render_begin + 16 passes + ccu_render_merge into the host double buffer" if world == 1 else
+                      "per rank: camera + render_begin + 16 passes; NCCL reduce; rank 0: ccu_render_merge of the 16*N-pass window into the host double buffer"}
 
     if rank != 0:
         if world > 1:

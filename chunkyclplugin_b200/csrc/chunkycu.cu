@@ -1181,6 +1181,14 @@ int ccu_render_reset_window(ccu_ctx *c) {
     return CCU_OK;
 }
 
+int ccu_render_set_window_spp(ccu_ctx *c, int32_t window_spp) {
+    if (!c) return fail(CCU_EINVAL, "ccu_render_set_window_spp: null context");
+    if (window_spp < 0) return fail(CCU_EINVAL, "ccu_render_set_window_spp: negative pass count");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->window_spp = window_spp;
+    return CCU_OK;
+}
+
 int ccu_render_device_buffer(ccu_ctx *c, void **device_ptr, int64_t *n_floats) {
     if (!c || !device_ptr) return fail(CCU_EINVAL, "ccu_render_device_buffer: null argument");
     std::lock_guard<std::mutex> lk(c->mu);

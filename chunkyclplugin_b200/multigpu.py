@@ -75,3 +75,16 @@ class SampleParallelRenderer:
         """One NCCL reduce of the window sums (24.9 MB at 1080p, 99.5 MB at 4K); mean over all passes on ``dst``."""
         self.ctx.render_sync()
         return combine_windows(self.accumulation_tensor(), local_spp, dst=dst)
+
+    def render_and_merge(self, seeds: Sequence[int], sample_buffer: Optional[np.ndarray], sample_spp: int, dst: int = 0) -> int:
+        """One multi-GPU window end to end: every rank renders its passes, one NCCL reduce, and ``dst`` alone merges the
+        result into the host double sample buffer (OpenClPathTracingRenderer.java:164-173 with passSpp = all ranks' passes).
+        Returns the number of passes merged (on every rank)."""
+        n_local = self.render_window(seeds)
+        _, total = self.reduce_window(n_local, dst=dst)
+        if self.rank == dst:
+            torch.cuda.current_stream(self.device).synchronize()      # the reduce ran on torch's stream
+            self.ctx.render_set_window_spp(total)
+            merged = self.ctx.render_merge(sample_buffer, sample_spp)
+            assert merged == total
+        return total

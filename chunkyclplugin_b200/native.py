@@ -62,6 +62,7 @@ SYMBOLS = {
     "ccu_render_read": (C.c_int, [_vp, _vp, _pi32]),
     "ccu_render_merge": (C.c_int, [_vp, _vp, _i32, _pi32]),
     "ccu_render_reset_window": (C.c_int, [_vp]),
+    "ccu_render_set_window_spp": (C.c_int, [_vp, _i32]),
     "ccu_render_end": (C.c_int, [_vp]),
     "ccu_render_device_buffer": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     "ccu_render_scale": (C.c_int, [_vp, _f]),
@@ -237,6 +238,9 @@ class Context:
 
     def render_reset_window(self):
         check(self._lib.ccu_render_reset_window(self._h))
+
+    def render_set_window_spp(self, window_spp: int):
+        check(self._lib.ccu_render_set_window_spp(self._h, int(window_spp)))
 
     def render_end(self):
         check(self._lib.ccu_render_end(self._h))

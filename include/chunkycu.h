@@ -96,6 +96,9 @@ int ccu_render_read(ccu_ctx *ctx, float *mean_rgb, int32_t *window_spp);
  *   sample[i] = (sample[i]*sample_spp + mean[i]*window_spp) / (sample_spp + window_spp); then the window restarts (:170) */
 int ccu_render_merge(ccu_ctx *ctx, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp);
 int ccu_render_reset_window(ccu_ctx *ctx); /* bufferSppReal = 0 (:170); the buffer itself is not cleared, as in the reference */
+/* multi-GPU: after the window buffers of all ranks have been reduced into this context's buffer (mean over all passes), tell it how
+ * many passes the buffer now stands for, so that ccu_render_merge / ccu_render_read weight it correctly (bufferSppReal of :167-173) */
+int ccu_render_set_window_spp(ccu_ctx *ctx, int32_t window_spp);
 int ccu_render_end(ccu_ctx *ctx);          /* releases the per-render buffers (:80-85 try-with-resources) */
 
 /* multi-GPU plumbing: device pointer of the running-mean buffer (float[3*W*H]) so that the host's

@@ -1,4 +1,6 @@
 #!/bin/bash
 make -C oracle CC=gcc >/dev/null
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "queue and (entities or mixed)" 2>&1 | tail -3
-for l in 2 4 8 12 16; do for b in 23 25; do echo -n "entities leaf_min=$l bvh_warps=$b: "; CCU_Q_LEAF_MIN=$l CCU_Q_BVH_WARPS=$b timeout 300 python scripts/run_render.py --scene entities --passes 4 --windows 2 --kernel 4 | grep "window 1"; done; done
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -3
+for y in 16 20; do echo -n "terrain yield=$y: "; CCU_YIELD_BELOW=$y timeout 300 python scripts/run_render.py --passes 8 --windows 2 --kernel 4 | grep "window 1"; done
+echo -n "indoor: "; timeout 300 python scripts/run_render.py --scene indoor --passes 8 --windows 2 --kernel 4 | grep "window 1"
+echo -n "entities: "; timeout 300 python scripts/run_render.py --scene entities --passes 4 --windows 2 --kernel 4 | grep "window 1"
