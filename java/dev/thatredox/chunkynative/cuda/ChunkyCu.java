@@ -179,6 +179,19 @@ public final class ChunkyCu {
         }
     }
 
+    /** Device name for the GPU selector (ui/GpuSelector.java:89-125 reads CL_DEVICE_NAME). */
+    public static String deviceName(int index) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment name = a.allocate(256);
+            check((int) DEVICE_INFO.invokeExact(index, name, 256, MemorySegment.NULL, MemorySegment.NULL, MemorySegment.NULL));
+            return name.getString(0);
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new RuntimeException(t);
+        }
+    }
+
     public static int deviceCount() {
         try (Arena a = Arena.ofConfined()) {
             MemorySegment n = a.allocate(JAVA_INT);

@@ -39,7 +39,7 @@ public class CudaPathTracingRenderer implements Renderer {
         Scene scene = manager.bufferedScene;
         double[] sampleBuffer = scene.getSampleBuffer();
         sceneLoader.ensureLoad(scene);
-        sceneLoader.uploadCamera(scene);                       // ClCamera: settings or pre-generated rays
+        sceneLoader.uploadCamera(scene, null, true);            // ClCamera: settings or pre-generated rays (jittered)
         ctx.renderBegin(scene.width, scene.height);
         try {
             int bufferSppReal = 0;
