@@ -555,7 +555,8 @@ struct TriRepack {
 int bvh_ref(const std::vector<int> &bvh, const std::vector<int> &trigs, size_t node, int depth, BvhLayout &b, TriRepack &tr,
             std::unordered_map<int, int> &leaf_map) {
     if (!b.ok) return -1;
-    if (node + 6 >= bvh.size() || depth > 256) { b.ok = false; return -1; }
+    // deeper than the traversal stack of the reference (int nodesToVisit[64], bvh.h:38): undefined there, refused here
+    if (node + 6 >= bvh.size() || depth >= 64) { b.ok = false; return -1; }
     const int head = bvh[node];
     if (head <= 0) {
         const int prim = -head;
@@ -973,6 +974,8 @@ static int render_ready(ccu_ctx *c, const char *what) {
     return CCU_OK;
 }
 
+static int render_passes_locked(ccu_ctx *c, const int32_t *seeds, int32_t n_passes, bool first_chunk);
+
 int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) {
     if (!c) return fail(CCU_EINVAL, "ccu_render_passes: null context");
     if (n_passes < 0 || (n_passes > 0 && !seeds)) return fail(CCU_EINVAL, "ccu_render_passes: bad seeds");
@@ -982,6 +985,17 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
     if (n_passes == 0) return CCU_OK;
     DeviceGuard g(c->device);
     stop_timer(c);
+    // one launch covers at most 32768 passes (the default kernel keeps a path's pass index in 16 bits); the reference's
+    // windows are at most 1024 passes (OpenClPathTracingRenderer.java:158)
+    const int32_t kChunk = 32768;
+    for (int32_t off = 0; off < n_passes; off += kChunk) {
+        rc = render_passes_locked(c, seeds + off, std::min(kChunk, n_passes - off), off == 0);
+        if (rc != CCU_OK) return rc;
+    }
+    return CCU_OK;
+}
+
+static int render_passes_locked(ccu_ctx *c, const int32_t *seeds, int32_t n_passes, bool first_chunk) {
     if (c->seeds_cap < n_passes) {
         cudaStreamSynchronize(c->stream);
         if (c->seeds_dev) cudaFree(c->seeds_dev);
@@ -996,7 +1010,7 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
     fill_scene(c);
     int n_pixels = c->width * c->height;
     if (!c->work_counter) CU(cudaMalloc(&c->work_counter, sizeof(unsigned int)));
-    CU(cudaEventRecord(c->ev0, c->stream));
+    if (first_chunk) CU(cudaEventRecord(c->ev0, c->stream));
     if (c->params.kernel != 1) CU(cudaMemsetAsync(c->work_counter, 0, sizeof(unsigned int), c->stream));
     const bool wide = c->scene.use_wide != 0;
     const bool bvh = !(c->scene.world_bvh_empty && c->scene.actor_bvh_empty);
@@ -1037,7 +1051,7 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
             const bool tops = c->air_top.n <= (size_t)Q_TOP_WORDS && getenv("CCU_NO_TOPS") == nullptr;
             const int grid = c->sm_count, block = Q_WARPS * 32;
             if (!c->use_air) return fail(CCU_ESTATE, "ccu_render_passes: kernel 4 needs the air layout (malformed octree?)");
-            if (bvh && !c->use_bvh2) return fail(CCU_ESTATE, "ccu_render_passes: kernel 4 needs the BVH stage layout (malformed BVH?)");
+            if (bvh && !c->use_bvh2) return fail(CCU_ESTATE, "ccu_render_passes: malformed BVH, or deeper than the 64 levels the reference's traversal stack holds (bvh.h:38)");
             if (tops) {
                 if (bvh) k_render_queue<true, true><<<grid, block, q_smem_bytes(true, true), c->stream>>>(c->scene, qp);
                 else k_render_queue<false, true><<<grid, block, q_smem_bytes(false, true), c->stream>>>(c->scene, qp);

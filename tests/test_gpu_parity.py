@@ -280,3 +280,17 @@ def test_one_context_shared_by_threads(scenes, cuda_ctx):
     assert not errs, errs
     got, spp = cuda_ctx.render_read()
     assert spp == 8 and np.array_equal(_bits(got), _bits(oracle.Oracle(p).render(seeds)))
+
+
+def test_batch_longer_than_one_launch(cuda_ctx):
+    """A single call with more passes than one launch covers (32768) is split internally; same running mean."""
+    import dataclasses
+    import oracle
+    from chunkyclplugin_b200 import scenes as S
+    p = dataclasses.replace(S.terrain_scene(64, 160, 90, seed=7), width=8, height=6)
+    seeds = pass_seeds(40000)
+    load_scene(cuda_ctx, p)
+    cuda_ctx.render_passes(seeds)
+    got, spp = cuda_ctx.render_read()
+    assert spp == 40000
+    assert np.array_equal(_bits(got), _bits(oracle.Oracle(p).render(seeds)))
