@@ -175,8 +175,9 @@ __global__ void k_gather_fill(uint4 *a, size_t sectors, uint32_t seed) {
         a[i] = make_uint4(h, h * 3u + 1u, h ^ 0x9e3779b9u, (uint32_t)i);
     }
 }
-__global__ void __launch_bounds__(256) k_gather(const uint4 *__restrict__ a, uint32_t sector_mask, int loads, int dependent, uint32_t *sink) {
-    uint32_t st = (blockIdx.x * blockDim.x + threadIdx.x) * 747796405u + 2891336453u;
+__global__ void __launch_bounds__(256) k_gather(const uint4 *__restrict__ a, uint32_t sector_mask, int loads, int dependent, uint32_t salt, uint32_t *sink) {
+    // salt: every timed launch walks different sectors, so that a repeat does not find its own footprint in L2
+    uint32_t st = (blockIdx.x * blockDim.x + threadIdx.x + salt * 0x9e3779b9u) * 747796405u + 2891336453u;
     uint32_t acc = 0;
     if (dependent) {
         // one thread per SM walks the chain: the time per load is the latency of one dependent gather
@@ -1363,7 +1364,7 @@ int ccu_bench_gather(ccu_ctx *c, int64_t array_bytes, int32_t dependent, float *
     float best = 1e30f;
     for (int it = 0; it < 4; it++) {   // first iteration warms the caches
         cudaEventRecord(c->ev0, c->stream);
-        k_gather<<<blocks, dependent ? 32 : 256, 0, c->stream>>>(a, (uint32_t)(sectors - 1), loads, dependent, sink);
+        k_gather<<<blocks, dependent ? 32 : 256, 0, c->stream>>>(a, (uint32_t)(sectors - 1), loads, dependent, (uint32_t)it, sink);
         cudaEventRecord(c->ev1, c->stream);
         e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) break;
