@@ -31,7 +31,13 @@ def main():
         print("reference kernel cannot run here:", why)
         return 1
     out = {"passes": N_PASSES, "scenes": {}}
-    for name, p in (("config1_terrain256", S.terrain_scene(256, 1920, 1080)), ("config3_indoor256", S.indoor_scene(256, 1920, 1080))):
+    which = os.environ.get("SCENES", "config1,config3").split(",")
+    scenes = []
+    if "config1" in which: scenes.append(("config1_terrain256", S.terrain_scene(256, 1920, 1080)))
+    if "config3" in which: scenes.append(("config3_indoor256", S.indoor_scene(256, 1920, 1080)))
+    if "config4" in which: scenes.append(("config4_entities256", S.entity_scene(256, 1920, 1080)))
+    builds = os.environ.get("BUILDS", "stock,strict").split(",")
+    for name, p in scenes:
         ctx = native.Context(0)
         ctx.scene_begin(); ctx.set_atlas(p.atlas); ctx.set_block_palette(p.block_palette); ctx.set_material_palette(p.mat_palette)
         ctx.set_aabb_models(p.aabb_models); ctx.set_quad_models(p.quad_models); ctx.set_triangles(p.bvh_trigs)
@@ -40,7 +46,7 @@ def main():
         ctx.camera_set(p.projector_type, p.camera); ctx.render_begin(p.width, p.height)
         seeds = pass_seeds(N_PASSES)
         res = {}
-        for build in ("stock", "strict"):
+        for build in builds:
             ref = clref.ClReference(p, strict=(build == "strict"))
             # ---- config 2: first-hit buffers of the full frame
             fh_ref = ref.first_hit(seeds[0])
@@ -76,7 +82,7 @@ def main():
         out["scenes"][name] = res
         ctx.close()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "clref_converged.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("OUT", "clref_converged.json")), "w"), indent=1)
     return 0
 
 
