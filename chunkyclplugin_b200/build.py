@@ -15,8 +15,9 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     # arithmetic contract: no contraction, IEEE division / sqrt, denormals kept
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "--threads", "2",
 ]
+LINK_FLAGS = ["-ldl"]   # NCCL is bound at run time (ccu_group.cu)
 
 
 def sources():
@@ -36,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     extra = os.environ.get("CCU_NVCC_EXTRA", "").split()
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources() + LINK_FLAGS
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)

@@ -22,10 +22,12 @@ struct DScene {
     const unsigned *__restrict__ wide;
     int cell_level, top_log2;
     int use_wide;
-    // march-loop ("air") layout: same table / node shape, entries carry only air-or-not + level, finest nodes are 128-bit maps
+    // march-loop ("air") layout, see ccu_march.cuh: top table over cells of level air_cell_level (>= 4), 64-ary nodes
+    // down to level 4 (deep worlds only), one 1-KiB brick of 2-bit voxel codes per 16^3 cell that is not a single leaf
     const unsigned *__restrict__ air_top;
     const unsigned *__restrict__ air_wide;
-    const unsigned *__restrict__ air_bits;
+    const unsigned *__restrict__ air_bricks;
+    int air_cell_level, air_top_log2;
     // palettes (reference packed layouts)
     const int *__restrict__ block_palette;
     int block_palette_len;
@@ -312,7 +314,7 @@ struct ModelHit {    // returned by value so that callers keep their state in re
 };
 
 // block.h:66-116: AABB models (type 2) and quad models (type 3).  Cold path, kept out of line.
-__device__ __noinline__ ModelHit intersect_model_block(const DScene &s, int model_type, int model_ptr, float3 norm_origin,
+static __device__ __noinline__ ModelHit intersect_model_block(const DScene &s, int model_type, int model_ptr, float3 norm_origin,
                                                        float3 direction, float3 inv) {
     ModelHit out;
     out.surf.normal = f3(0, 0, 0);
@@ -456,22 +458,7 @@ __device__ __forceinline__ void march_exit(March &m, const Cell &c, int level) {
     m.t += box_exit(leaf, c.q, m.inv) + CCU_OFFSET;
     m.steps++;
 }
-// First half of one iteration of octree.h:66-107: locate the leaf under the ray.
-// Returns 0 = air leaf, already left (keep marching); 1 = non-air leaf found (data/level/node set, ray not advanced);
-// 2 = the ray is finished without a hit (step limit, beyond the record's distance, or outside the cube).
-template <bool WIDE>
-__device__ __forceinline__ int march_probe(const DScene &s, March &m, int &data, int &level, int &node) {
-    if (m.steps >= s.draw_depth || m.t > m.limit) return 2;
-    const int depth = s.depth;
-    Cell c = march_cell(m);
-    if (((c.bx >> depth) | (c.by >> depth) | (c.bz >> depth)) != 0) return 2;
-    if (WIDE) { data = find_leaf_wide(s, c.bx, c.by, c.bz, level); node = -1; }
-    else data = find_leaf(s, c.bx, c.by, c.bz, level, node);
-    if (data != 0) return 1;   // ray->material is always 0 (wavefront.h:34)
-    march_exit(m, c, level);
-    return 0;
-}
-// Second half: test the non-air leaf found by march_probe.  Returns true on a hit (surf / hit_t filled);
+// Block test of the non-air leaf under the ray (octree.h:92-106).  Returns true on a hit (surf / hit_t filled);
 // otherwise the ray has been advanced past the leaf.
 __device__ __forceinline__ bool march_block(const DScene &s, March &m, int data, int level, Surf &surf, float &hit_t) {
     Cell c = march_cell(m);
@@ -484,13 +471,19 @@ __device__ __forceinline__ bool march_block(const DScene &s, March &m, int data,
     return false;
 }
 
-// One whole iteration.  Returns 0 = keep marching, 1 = hit (hit_t / surf / block / node filled), 2 = ray left.
-template <bool WIDE>
-__device__ __forceinline__ int march_step(const DScene &s, March &m, Surf &surf, float &hit_t, int &hit_block, int &hit_node, Cell &hit_cell) {
-    int data, level, node;
-    int r = march_probe<WIDE>(s, m, data, level, node);
-    if (r != 1) return r;
+// One whole iteration of octree.h:66-107 on the reference's own node array (root descent per step).
+// Returns 0 = keep marching, 1 = hit (hit_t / surf / block / node filled), 2 = ray left.
+__device__ __forceinline__ int march_step_ref(const DScene &s, March &m, Surf &surf, float &hit_t, int &hit_block, int &hit_node, Cell &hit_cell) {
+    if (m.steps >= s.draw_depth || m.t > m.limit) return 2;
+    const int depth = s.depth;
     const Cell c = march_cell(m);
+    if (((c.bx >> depth) | (c.by >> depth) | (c.bz >> depth)) != 0) return 2;
+    int level, node;
+    const int data = find_leaf(s, c.bx, c.by, c.bz, level, node);
+    if (data == 0) {           // ray->material is always 0 (wavefront.h:34)
+        march_exit(m, c, level);
+        return 0;
+    }
     if (march_block(s, m, data, level, surf, hit_t)) {
         hit_block = data;
         hit_node = node;
@@ -500,15 +493,14 @@ __device__ __forceinline__ int march_step(const DScene &s, March &m, Surf &surf,
     return 0;
 }
 
-template <bool WIDE>
-__device__ __forceinline__ bool octree_intersect(const DScene &s, float3 origin, float3 direction, Record &rec, HitInfo &hi) {
+__device__ __forceinline__ bool octree_intersect_ref(const DScene &s, float3 origin, float3 direction, Record &rec, HitInfo &hi) {
     March m;
     if (!march_begin(s, m, origin, direction, rec.distance)) return false;
     for (;;) {
         float t;
         int block, node;
         Cell cell;
-        int r = march_step<WIDE>(s, m, rec.surf, t, block, node, cell);
+        int r = march_step_ref(s, m, rec.surf, t, block, node, cell);
         if (r == 1) {
             rec.distance = t;
             rec.material = block;
@@ -529,7 +521,7 @@ struct BvhHit {
     Surf surf;
 };
 
-__device__ __noinline__ BvhHit bvh_intersect(const DScene &s, const int *__restrict__ bvh, float3 origin, float3 direction, float limit) {
+static __device__ __noinline__ BvhHit bvh_intersect(const DScene &s, const int *__restrict__ bvh, float3 origin, float3 direction, float limit) {
     BvhHit out;
     out.dist = nanf_();
     out.surf.normal = f3(0, 0, 0);
@@ -602,10 +594,9 @@ __device__ __forceinline__ bool bvh_pair(const DScene &s, float3 origin, float3 
     return hit;
 }
 
-// kernel.h:14-24
-template <bool WIDE>
-__device__ __forceinline__ bool closest_intersect(const DScene &s, float3 origin, float3 direction, Record &rec, HitInfo &hi) {
-    bool hit = octree_intersect<WIDE>(s, origin, direction, rec, hi);
+// kernel.h:14-24 on the reference's own node array
+__device__ __forceinline__ bool closest_intersect_ref(const DScene &s, float3 origin, float3 direction, Record &rec, HitInfo &hi) {
+    bool hit = octree_intersect_ref(s, origin, direction, rec, hi);
     int kind = 0;
     if (bvh_pair(s, origin, direction, rec.distance, rec.surf, kind)) {
         hit = true;
@@ -717,60 +708,6 @@ __device__ __forceinline__ float3 diffuse_direction(float3 n, float x1, float x2
     float vy = uz * n.x - ux * n.z;
     float vz = ux * n.y - uy * n.x;
     return f3((ux * tx + vx * ty) + n.x * tz, (uy * tx + vy * ty) + n.y * tz, (uz * tx + vz * ty) + n.z * tz);
-}
-
-// one path sample for pixel gid, thread-sequential: rayTracer.cl:40-107 (+ kernel.h:33-98, sky.h:68-93)
-template <bool WIDE>
-__device__ __forceinline__ float3 sample_pixel(const DScene &s, int gid, int seed) {
-    float3 color = f3(0, 0, 0), throughput = f3(1, 1, 1);
-    int ray_depth = 0;
-    uint32_t rng = (uint32_t)seed + (uint32_t)gid;
-    rng_next(rng);
-    float3 origin, direction;
-    camera_ray<false>(s, gid, rng, origin, direction);
-    Record rec;
-    rec.distance = inff_();
-    rec.material = 0;
-    rec.point = f3(0, 0, 0);
-    rec.surf.normal = f3(0, 0, 0);
-    rec.surf.color = make_float4(0, 0, 0, 0);
-    rec.surf.emittance = 0;
-    HitInfo hi = {-1, 0, 0, 0, 0};
-    for (;;) {
-        if (!closest_intersect<WIDE>(s, origin, direction, rec, hi)) {
-            // miss: emittance = 1, sky (+ sun disc) added through the throughput (rayTracer.cl:95-97, kernel.h:26-31)
-            float3 sky = sky_radiance(s, direction);
-            color = color + (sky * throughput) * 1.0f;
-            break;
-        }
-        // kernel.h:33-44
-        origin = rec.point;
-        float3 col = f3(rec.surf.color.x, rec.surf.color.y, rec.surf.color.z);
-        throughput = throughput * col;
-        color = color + (col * (rec.surf.emittance * s.emitter_scale)) * throughput;
-        // sun sampling + shadow ray (sky.h:68-93, rayTracer.cl:101-106)
-        if (s.sun_flags & 1) {
-            float x1 = rng_float(rng);
-            float x2 = rng_float(rng);
-            float3 d = sun_sample_direction(s, x1, x2);
-            float shadow_emittance = fabsf(dot3(d, rec.surf.normal));
-            Record sh = rec;                          // keeps the surface hit's distance as the ray limit
-            HitInfo shi;
-            if (!closest_intersect<WIDE>(s, origin, d, sh, shi)) {
-                float3 sky = sky_radiance(s, d);
-                color = color + (sky * throughput) * shadow_emittance;
-            }
-        }
-        // kernel.h:46-98 diffuse bounce
-        float x1 = rng_float(rng);
-        float x2 = rng_float(rng);
-        direction = diffuse_direction(rec.surf.normal, x1, x2);
-        origin = rec.point + direction * CCU_OFFSET;
-        ray_depth += 1;
-        rec.distance = inff_();
-        if (!(ray_depth < s.max_depth)) break;
-    }
-    return color;
 }
 
 }  // namespace ccu

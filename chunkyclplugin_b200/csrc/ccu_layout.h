@@ -1,0 +1,285 @@
+// ccu_layout.h - commit-time layout builders (host C++): the value-carrying octree layout, the march ("air") layout and
+// the BVH stage layout.  Included by chunkycu.cu only.
+#pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <unordered_map>
+#include <vector>
+
+#include "ccu_device.cuh"
+#include "ccu_march.cuh"
+
+
+// ------------------------------------------------------------------------------------------------------
+// commit-time traversal layout (see DScene::top / DScene::wide)
+// ------------------------------------------------------------------------------------------------------
+namespace {
+struct WideLayout {
+    std::vector<unsigned> top, wide;
+    int cell_level = 0, top_log2 = 0;
+    bool ok = true;
+};
+
+inline unsigned wide_leaf(int word, int level, bool &ok) {
+    long long v = -(long long)word;
+    unsigned val;
+    if (v == 0x7FFFFFFELL) val = CCU_WIDE_ANY;
+    else if (v >= 0 && v < (long long)CCU_WIDE_ANY) val = (unsigned)v;
+    else { ok = false; val = 0; }
+    return CCU_WIDE_LEAF | ((unsigned)level << 26) | val;
+}
+
+unsigned wide_node(const int *tree, size_t n, int word, int lvl, WideLayout &b) {
+    if (lvl < 2 || (size_t)word + 7 >= n) { b.ok = false; return wide_leaf(0, 0, b.ok); }
+    const size_t idx = b.wide.size() / 64;
+    if (idx >= 0x7FFFFFFFu) { b.ok = false; return wide_leaf(0, 0, b.ok); }
+    b.wide.resize(b.wide.size() + 64);
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++)
+            for (int k = 0; k < 4; k++) {
+                unsigned e;
+                int c1 = tree[(size_t)word + ((((i >> 1) & 1) << 2) | (((j >> 1) & 1) << 1) | ((k >> 1) & 1))];
+                if (c1 <= 0) {
+                    e = wide_leaf(c1, lvl - 1, b.ok);
+                } else if ((size_t)c1 + 7 >= n) {
+                    b.ok = false;
+                    e = wide_leaf(0, 0, b.ok);
+                } else {
+                    int c2 = tree[(size_t)c1 + (((i & 1) << 2) | ((j & 1) << 1) | (k & 1))];
+                    e = c2 <= 0 ? wide_leaf(c2, lvl - 2, b.ok) : wide_node(tree, n, c2, lvl - 2, b);
+                }
+                b.wide[idx * 64 + ((i << 4) | (j << 2) | k)] = e;
+            }
+    return (unsigned)idx;
+}
+
+// "Air layout" for the march loop (ccu_march.cuh): top table over cells of level `cell_level` (>= 4), 64-ary nodes down to
+// level 4 for deep worlds, and one 1-KiB brick of 2-bit voxel codes per 16^3 cell that is not a single leaf.  The march loop
+// needs nothing else (octree.h:89-106: an air leaf is left through its cube, anything else goes to the block test); a leaf
+// lookup is one table load plus at most one brick load.
+struct AirLayout {
+    std::vector<unsigned> top, wide, bricks;
+    int cell_level = 4, top_log2 = 0;
+    bool ok = true;
+};
+
+inline unsigned air_leaf(int word, int level) { return CCU_WIDE_LEAF | ((word == 0 ? (unsigned)level : 31u) << 26); }
+inline int oct_child(int x, int y, int z) { return ((x & 1) << 2) | ((y & 1) << 1) | (z & 1); }
+
+// brick of the 16^3 cell rooted at the branch node `word` (level 4)
+unsigned air_brick(const int *tree, size_t n, int word, AirLayout &b) {
+    const size_t idx = b.bricks.size() / 256;
+    if (idx >= 0x7FFFFFu || (size_t)word + 7 >= n) { b.ok = false; return air_leaf(1, 0); }
+    b.bricks.resize(b.bricks.size() + 256, 0u);
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++)
+            for (int k = 0; k < 4; k++) {
+                unsigned *blk = &b.bricks[idx * 256 + (size_t)((i << 4) | (j << 2) | k) * 4];
+                unsigned uniform = 0;
+                bool mixed = false;
+                int c2 = 0;
+                const int c1 = tree[(size_t)word + oct_child(i >> 1, j >> 1, k >> 1)];        // level 3
+                if (c1 <= 0) {
+                    uniform = c1 == 0 ? (CCU_BRICK_UNIFORM | 3u) : 0u;
+                } else if ((size_t)c1 + 7 >= n) {
+                    b.ok = false;
+                } else {
+                    c2 = tree[(size_t)c1 + oct_child(i, j, k)];                               // level 2
+                    if (c2 <= 0) uniform = c2 == 0 ? (CCU_BRICK_UNIFORM | 2u) : 0u;
+                    else if ((size_t)c2 + 7 >= n) b.ok = false;
+                    else mixed = true;
+                }
+                if (!mixed) {
+                    blk[0] = blk[1] = blk[2] = blk[3] = uniform;
+                    continue;
+                }
+                for (int x = 0; x < 4; x++)
+                    for (int y = 0; y < 4; y++)
+                        for (int z = 0; z < 4; z++) {
+                            unsigned code;
+                            const int d1 = tree[(size_t)c2 + oct_child(x >> 1, y >> 1, z >> 1)];   // level 1
+                            if (d1 <= 0) {
+                                code = d1 == 0 ? 2u : 0u;
+                            } else if ((size_t)d1 + 7 >= n) {
+                                b.ok = false;
+                                code = 0;
+                            } else {
+                                const int d2 = tree[(size_t)d1 + oct_child(x, y, z)];              // level 0
+                                if (d2 > 0) b.ok = false;                                           // deeper than the declared depth
+                                code = d2 == 0 ? 1u : 0u;
+                            }
+                            blk[x] |= code << ((((y << 2) | z)) * 2);
+                        }
+            }
+    return (unsigned)idx;
+}
+
+unsigned air_node(const int *tree, size_t n, int word, int lvl, AirLayout &b) {
+    if (lvl == 4) return air_brick(tree, n, word, b);
+    if (lvl < 6 || (size_t)word + 7 >= n) { b.ok = false; return air_leaf(1, 0); }
+    const size_t idx = b.wide.size() / 64;
+    if (idx >= 0x1FFFFFFu) { b.ok = false; return air_leaf(1, 0); }
+    b.wide.resize(b.wide.size() + 64);
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++)
+            for (int k = 0; k < 4; k++) {
+                unsigned e;
+                const int c1 = tree[(size_t)word + oct_child(i >> 1, j >> 1, k >> 1)];
+                if (c1 <= 0) {
+                    e = air_leaf(c1, lvl - 1);
+                } else if ((size_t)c1 + 7 >= n) {
+                    b.ok = false;
+                    e = air_leaf(1, 0);
+                } else {
+                    const int c2 = tree[(size_t)c1 + oct_child(i, j, k)];
+                    e = c2 <= 0 ? air_leaf(c2, lvl - 2) : air_node(tree, n, c2, lvl - 2, b);
+                }
+                b.wide[idx * 64 + ((i << 4) | (j << 2) | k)] = e;
+            }
+    return (unsigned)idx;
+}
+
+// Octrees shallower than a brick (depth < 4): one brick whose corner [0, 2^depth)^3 holds the tree, filled voxel by voxel
+// from the root descent (octree.h:81-88); the march loop never looks outside the cube (bounds check octree.h:76-78).
+void air_small_brick(const int *tree, size_t n, int depth, AirLayout &b) {
+    b.bricks.assign(256, 0u);
+    const int size = 1 << depth;
+    for (int x = 0; x < size; x++)
+        for (int y = 0; y < size; y++)
+            for (int z = 0; z < size; z++) {
+                int level = depth, word = tree[0];
+                while (word > 0 && level > 0) {
+                    level--;
+                    const size_t at = (size_t)word + oct_child(x >> level, y >> level, z >> level);
+                    if (at >= n) { b.ok = false; word = -1; break; }
+                    word = tree[at];
+                }
+                if (word > 0) { b.ok = false; word = -1; }
+                unsigned *blk = &b.bricks[(size_t)((((x >> 2) & 3) << 4) | (((y >> 2) & 3) << 2) | ((z >> 2) & 3)) * 4];
+                if (word == 0 && level >= 2) {
+                    blk[x & 3] = CCU_BRICK_UNIFORM | (unsigned)level;
+                } else {
+                    const unsigned code = word == 0 ? (unsigned)level + 1u : 0u;
+                    blk[x & 3] |= code << (((((y & 3) << 2) | (z & 3))) * 2);
+                }
+            }
+}
+
+AirLayout build_air_layout(const int *tree, size_t n, int depth) {
+    AirLayout b;
+    if (depth < 4) {
+        b.cell_level = 4;
+        b.top_log2 = 0;
+        if (tree[0] <= 0) b.top.assign(1, air_leaf(tree[0], depth));
+        else { b.top.assign(1, 0u); air_small_brick(tree, n, depth, b); }
+    } else {
+        int cl = std::max(depth - 7, 4);             // top table of at most 128^3 cells
+        if (cl & 1) cl++;
+        if (cl > depth) cl = depth & ~1;
+        b.cell_level = cl;
+        b.top_log2 = depth - cl;
+        const int dim = 1 << b.top_log2;
+        b.top.assign((size_t)dim * dim * dim, 0u);
+        for (int x = 0; x < dim && b.ok; x++)
+            for (int y = 0; y < dim; y++)
+                for (int z = 0; z < dim; z++) {
+                    int level = depth;
+                    int word = tree[0];
+                    while (word > 0 && level > cl) {
+                        level--;
+                        const int sh = level - cl;
+                        const size_t at = (size_t)word + oct_child(x >> sh, y >> sh, z >> sh);
+                        if (at >= n) { b.ok = false; word = 0; break; }
+                        word = tree[at];
+                    }
+                    b.top[((size_t)x * dim + y) * dim + z] = word <= 0 ? air_leaf(word, level) : air_node(tree, n, word, cl, b);
+                }
+    }
+    if (b.wide.empty()) b.wide.assign(64, air_leaf(1, 0));
+    if (b.bricks.empty()) b.bricks.assign(256, 0u);
+    return b;
+}
+
+// Traversal layout of a packed BVH (PackedBvhNode.java:22-31: 7 ints per node, first child at node + 7, second child at
+// node[0]) for the BVH stage of ccu_queue.cuh: one 64-byte record per inner node holding BOTH children's boxes
+// (bvh.h:73-91 fetches exactly those at every inner node) and a reference per child, and 16-byte aligned triangle
+// blocks.  ref >= 0: record index; ref < 0: leaf, -(1 + offset of its block in `tris`, in units of 4 words).
+struct BvhLayout {
+    std::vector<int> rec;
+    int root = 0;
+    bool ok = true;
+};
+struct TriRepack {
+    std::vector<int> tris;                       // per leaf: {count, 0, 0, 0} + count x 20 words (PackedTriangle.java:46-78)
+    int add(const std::vector<int> &trigs, int prim, bool &ok) {
+        if (prim < 0 || (size_t)prim >= trigs.size()) { ok = false; return 0; }
+        const int count = trigs[(size_t)prim];
+        if (count < 0 || (size_t)prim + 1 + (size_t)count * 20 > trigs.size()) { ok = false; return 0; }
+        const int off = (int)(tris.size() / 4);
+        tris.push_back(count); tris.push_back(0); tris.push_back(0); tris.push_back(0);
+        tris.insert(tris.end(), trigs.begin() + prim + 1, trigs.begin() + prim + 1 + (size_t)count * 20);
+        return off;
+    }
+};
+
+int bvh_ref(const std::vector<int> &bvh, const std::vector<int> &trigs, size_t node, int depth, BvhLayout &b, TriRepack &tr,
+            std::unordered_map<int, int> &leaf_map) {
+    if (!b.ok) return -1;
+    // deeper than the traversal stack of the reference (int nodesToVisit[64], bvh.h:38): undefined there, refused here
+    if (node + 6 >= bvh.size() || depth >= 64) { b.ok = false; return -1; }
+    const int head = bvh[node];
+    if (head <= 0) {
+        const int prim = -head;
+        auto it = leaf_map.find(prim);   // a leaf block referenced twice (both BVHs share the palette) is stored once
+        int off;
+        if (it != leaf_map.end()) {
+            off = it->second;
+        } else {
+            off = tr.add(trigs, prim, b.ok);
+            leaf_map.emplace(prim, off);
+        }
+        return -(1 + off);
+    }
+    const size_t left = node + 7, right = (size_t)head;
+    if (left + 6 >= bvh.size() || right + 6 >= bvh.size()) { b.ok = false; return -1; }
+    const size_t r = b.rec.size() / 16;
+    b.rec.resize(b.rec.size() + 16, 0);
+    for (int i = 0; i < 6; i++) {
+        b.rec[r * 16 + i] = bvh[left + 1 + i];
+        b.rec[r * 16 + 6 + i] = bvh[right + 1 + i];
+    }
+    const int rl = bvh_ref(bvh, trigs, left, depth + 1, b, tr, leaf_map);
+    const int rr = bvh_ref(bvh, trigs, right, depth + 1, b, tr, leaf_map);
+    b.rec[r * 16 + 12] = rl;
+    b.rec[r * 16 + 13] = rr;
+    return (int)r;
+}
+
+WideLayout build_wide_layout(const int *tree, size_t n, int depth) {
+    WideLayout b;
+    int cl = std::max(depth - 7, 4);
+    if (const char *e = getenv("CCU_CELL_LEVEL")) cl = std::max(0, atoi(e));   // tuning knob: level of the top table's cells
+    if (cl & 1) cl++;
+    if (cl > depth) cl = depth & ~1;
+    b.cell_level = cl;
+    b.top_log2 = depth - cl;
+    const int dim = 1 << b.top_log2;
+    b.top.assign((size_t)dim * dim * dim, 0u);
+    for (int x = 0; x < dim && b.ok; x++)
+        for (int y = 0; y < dim; y++)
+            for (int z = 0; z < dim; z++) {
+                int level = depth;
+                int word = tree[0];
+                while (word > 0 && level > cl) {
+                    level--;
+                    int sh = level - cl;
+                    size_t at = (size_t)word + ((((x >> sh) & 1) << 2) | (((y >> sh) & 1) << 1) | ((z >> sh) & 1));
+                    if (at >= n) { b.ok = false; word = 0; break; }
+                    word = tree[at];
+                }
+                b.top[((size_t)x * dim + y) * dim + z] = word <= 0 ? wide_leaf(word, level, b.ok) : wide_node(tree, n, word, cl, b);
+            }
+    if (b.wide.empty()) b.wide.assign(64, wide_leaf(0, 0, b.ok));
+    return b;
+}
+}  // namespace

@@ -25,7 +25,7 @@
 // Scheduling does not touch arithmetic: every path performs exactly the operations of the thread-per-pixel
 // kernel in the same order (RNG draw order, per-pixel pass order), so the image is bit-identical.
 #pragma once
-#include "ccu_wavefront.cuh"
+#include "ccu_march.cuh"
 
 #ifndef CCU_Q_WARPS
 #define CCU_Q_WARPS 28
@@ -88,8 +88,18 @@ __device__ unsigned long long g_qstats[32];   // [16] BVH stage entries, [18] BV
 #define QSTAT_LANE(i, v) do { } while (0)
 #endif
 
+struct PassParams {
+    const int *seeds;           // one seed per pass of this launch (rayTracer.cl:55)
+    int n_passes;
+    int start_spp;              // passes already in the accumulation window (bufferSpp, rayTracer.cl:109-112)
+    float *res;                 // running mean float[3*W*H]
+    const float *res_prev;      // buffer that holds the previous window's mean (what the reference's single buffer would hold at bufferSpp = 0)
+    int n_pixels;
+    unsigned int *next_pixel;   // global work counter (zeroed before the launch)
+};
+
 struct QueueParams {
-    WaveParams w;
+    PassParams w;
     int yield_below;   // MARCH: consider switching stage once fewer lanes than this are busy
     int refill_min;    // MARCH: hand over / refill once this many lanes hold a finished ray
     int leaf_min;      // BVH: process leaves once this many walks wait at one
@@ -97,67 +107,6 @@ struct QueueParams {
     int march_warps;   // scheduler: only warps 0 .. march_warps-1 run the MARCH stage
     int march_bias;    // scheduler: warps of sub-partitions 0..2 count MARCH columns +bias, warps of sub-partition 3 -bias
 };
-
-// ------------------------------------------------------------------------------------------------------
-// lean march step: the arithmetic of octree.h:66-107 for an air leaf, with the loop invariants hoisted
-// ------------------------------------------------------------------------------------------------------
-struct LeanRay {
-    float3 o, d, inv, doff;   // doff = d * OFFSET (octree.h:73, loop invariant)
-    float t, limit;
-    int steps;
-    int farx, fary, farz;     // 1 when the leaf cube is left through its upper plane on that axis
-};
-
-__device__ __forceinline__ void lean_prepare(LeanRay &r) {
-    r.doff = r.d * CCU_OFFSET;
-    r.farx = r.inv.x < 0.0f ? 0 : 1;
-    r.fary = r.inv.y < 0.0f ? 0 : 1;
-    r.farz = r.inv.z < 0.0f ? 0 : 1;
-}
-
-// AABB_exit (primitives.h:52-61) along one axis for a point q strictly inside [lo, hi): fmax((lo-q)*inv, (hi-q)*inv).
-// lo - q <= 0 < hi - q, so the maximum is the (hi-q)*inv term for inv >= 0 and the (lo-q)*inv term for inv < 0;
-// the only case where that term is NaN while the reference's fmax is not is inv = -inf with q == lo, where the
-// reference yields the other term, -inf: fmaxf(x, -inf) maps exactly that NaN to -inf and leaves every other x alone.
-__device__ __forceinline__ float lean_exit_axis(int b, int level, int far, float q, float inv) {
-    float plane = (float)(((b >> level) + far) << level);
-    return fmaxf((plane - q) * inv, -inff_());
-}
-
-// One iteration of octree.h:66-107 on the air layout (DScene::air_*).  Returns 0 = air leaf left (keep marching),
-// 1 = non-air leaf reached (ray not advanced; the block stage looks the leaf up), 2 = ray finished without a hit.
-// `top` is the air top table (shared or global).
-__device__ __forceinline__ int lean_probe(const DScene &s, const unsigned *__restrict__ top, LeanRay &r) {
-    if (r.steps >= s.draw_depth || r.t > r.limit) return 2;
-    float3 pos = r.o + r.d * r.t;
-    float3 q = pos + r.doff;
-    int bx = f2i(floorf(q.x)), by = f2i(floorf(q.y)), bz = f2i(floorf(q.z));
-    if (((bx | by | bz) >> s.depth) != 0) return 2;
-    const int cl = s.cell_level;
-    unsigned e = top[((((unsigned)(bx >> cl) << s.top_log2) + (unsigned)(by >> cl)) << s.top_log2) + (unsigned)(bz >> cl)];
-    // structured so that the lanes of a warp reconverge before the exit arithmetic: every path ends in a leaf entry
-    if (!(e & CCU_WIDE_LEAF)) {
-        int lvl = cl;
-        while (lvl > 2 && !(e & CCU_WIDE_LEAF)) {
-            lvl -= 2;
-            e = __ldg(s.air_wide + (e * 64u + (unsigned)((((bx >> lvl) & 3) << 4) | (((by >> lvl) & 3) << 2) | ((bz >> lvl) & 3))));
-        }
-        if (!(e & CCU_WIDE_LEAF)) {
-            // 4^3 voxels, 2 bits each: 0 = not air, 1 = air leaf of level 0, 2 = air leaf of level 1
-            const unsigned v = (unsigned)(((bx & 3) << 4) | ((by & 3) << 2) | (bz & 3));
-            const unsigned code = (__ldg(s.air_bits + (e * 4u + (v >> 4))) >> ((v & 15u) * 2u)) & 3u;
-            e = CCU_WIDE_LEAF | (code == 0 ? 1u : ((code - 1u) << 26));
-        }
-    }
-    if (e & 1u) return 1;
-    const int level = (e >> 26) & 31;
-    float ex = lean_exit_axis(bx, level, r.farx, q.x, r.inv.x);
-    float ey = lean_exit_axis(by, level, r.fary, q.y, r.inv.y);
-    float ez = lean_exit_axis(bz, level, r.farz, q.z, r.inv.z);
-    r.t += fminf(ex, fminf(ey, ez)) + CCU_OFFSET;
-    r.steps++;
-    return 0;
-}
 
 // ------------------------------------------------------------------------------------------------------
 // work masks: one qmask_t per stage and column, word index stage * 32 + column, bit = row
@@ -217,22 +166,23 @@ __device__ __forceinline__ void q_load_lean(const uint32_t *F, int slot, LeanRay
     lean_prepare(r);
 }
 
-// MARCH (NST = number of stages of this kernel)
-template <int NST>
+// MARCH (NST = number of stages of this kernel; LAY: 0 = top table in shared memory, 1 = in global memory, 2 = deep world)
+template <int NST, int LAY>
 __device__ __forceinline__ void q_stage_march(const DScene &s, const unsigned *__restrict__ top, uint32_t *F, unsigned *mask, int lane,
                                               int yield_below, int refill_min) {
     const unsigned full = 0xffffffffu;
     int cur = -1;   // slot of the ray this lane is marching (row * 32 + column), -1 = none
     LeanRay r;
     r.o = r.d = r.inv = r.doff = f3(0, 0, 0);
-    r.t = 0; r.limit = 0; r.steps = 0; r.farx = r.fary = r.farz = 0;
+    r.t = 0; r.limit = 0; r.steps = 0; r.fmx = r.fmy = r.fmz = 0;
     int done = 0;   // 0 = ray in flight, 1 = reached a non-air leaf, 2 = finished
     int recheck = 0;
-    int n_done = 0, n_fly = 0;   // lanes holding a finished ray / a ray in flight (warp-uniform)
+    int busy = 0;   // lanes that hold a ray, in flight or finished (warp-uniform, changes only at a refill)
+    int n_fly = 0;  // lanes whose ray is in flight (warp-uniform)
     for (;;) {
         // Finished rays are handed over and idle lanes re-filled in batches: once refill_min lanes hold a finished
         // ray, or nothing is in flight.
-        if (n_done >= refill_min || n_fly == 0) {
+        if (busy - n_fly >= refill_min || n_fly == 0) {
             if (cur < 0 || done != 0) {
                 if (cur >= 0) {
                     F[QF_T * Q_SLOTS + cur] = __float_as_uint(r.t);
@@ -244,7 +194,7 @@ __device__ __forceinline__ void q_stage_march(const DScene &s, const unsigned *_
                 cur = row < 0 ? -1 : row * 32 + lane;
                 if (cur >= 0) q_load_lean(F, cur, r);
             }
-            const int busy = __popc(__ballot_sync(full, cur >= 0));
+            busy = __popc(__ballot_sync(full, cur >= 0));
             if (busy == 0) return;
             if (busy < yield_below) {
                 // few busy lanes: switch when another stage has more lanes' worth of work than this warp is using
@@ -258,11 +208,9 @@ __device__ __forceinline__ void q_stage_march(const DScene &s, const unsigned *_
                 recheck--;
             }
         }
-        if (cur >= 0 && done == 0) done = lean_probe(s, top, r);
-        const unsigned fly = __ballot_sync(full, cur >= 0 && done == 0);
-        n_fly = __popc(fly);
+        if (cur >= 0 && done == 0) done = lean_probe<LAY == 2, LAY == 0>(s, top, r);
+        n_fly = __popc(__ballot_sync(full, cur >= 0 && done == 0));
         QSTAT(10, 1); QSTAT(11, n_fly);
-        n_done = __popc(__ballot_sync(full, cur >= 0 && done != 0));
     }
     // park the rays still in flight, hand over the finished ones
     if (cur >= 0) {
@@ -595,7 +543,7 @@ __device__ __forceinline__ int tile_order_pixel(unsigned k, int W, int H) {
 }
 
 // rayTracer.cl:109-112, then the next pass / pixel: rayTracer.cl:55-91
-__device__ __forceinline__ void q_stage_end(const DScene &s, const WaveParams &w, uint32_t *F, unsigned *mask, int *live, int lane) {
+__device__ __forceinline__ void q_stage_end(const DScene &s, const PassParams &w, uint32_t *F, unsigned *mask, int *live, int lane) {
     const unsigned full = 0xffffffffu;
     const int row = q_pop(mask, QS_END, lane);
     QSTAT(2 * QS_END, 1); QSTAT(2 * QS_END + 1, __popc(__ballot_sync(full, row >= 0)));
@@ -608,9 +556,12 @@ __device__ __forceinline__ void q_stage_end(const DScene &s, const WaveParams &w
         // the running mean of this pixel is only ever touched by the slot that owns the pixel; L2 accesses keep it
         // coherent between the warps that run the slot's END stages
         float *px = w.res + (size_t)gid * 3;
-        float3 mean = f3(__ldcg(px), __ldcg(px + 1), __ldcg(px + 2));
-        float3 color = f3(QFL(QF_COLX), QFL(QF_COLY), QFL(QF_COLZ));
         int spp = w.start_spp + pass;
+        // at the start of a window the reference's buffer still holds the previous window's mean (it is multiplied by
+        // spp = 0, rayTracer.cl:111); with two window buffers that value lives in the other one
+        const float *pr = spp == 0 ? w.res_prev + (size_t)gid * 3 : px;
+        float3 mean = f3(__ldcg(pr), __ldcg(pr + 1), __ldcg(pr + 2));
+        float3 color = f3(QFL(QF_COLX), QFL(QF_COLY), QFL(QF_COLZ));
         float fs = (float)spp, fs1 = (float)(spp + 1);
         mean.x = (mean.x * fs + color.x) / fs1;
         mean.y = (mean.y * fs + color.y) / fs1;
@@ -679,8 +630,9 @@ __device__ __forceinline__ void q_stage_end(const DScene &s, const WaveParams &w
     q_store_ray(F, mask, lane, row, m, entered);
 }
 
-// TOPS: the top table of the air layout fits Q_TOP_WORDS and is staged in shared memory
-template <bool HAS_BVH, bool TOPS>
+// LAY 0: the top table of the air layout fits Q_TOP_WORDS and is staged in shared memory; 1: it is read from global memory;
+// 2: deep world (64-ary nodes between the top table and the bricks)
+template <bool HAS_BVH, int LAY>
 __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_constant__ DScene s, const __grid_constant__ QueueParams qp) {
     constexpr int NST = q_stages(HAS_BVH);
     constexpr int MASK_WORDS = q_mask_words(HAS_BVH);
@@ -695,8 +647,8 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
     for (int i = threadIdx.x; i < Q_SLOTS; i += blockDim.x) F[QF_META * Q_SLOTS + i] = QM_NEEDPIX;
     for (int i = threadIdx.x; i < NST * 32; i += blockDim.x)
         reinterpret_cast<qmask_t *>(mask)[i] = (i / 32 == QS_END) ? (Q_ROWS == 8 * (int)sizeof(qmask_t) ? ~qmask_t(0) : ((qmask_t(1) << Q_ROWS) - 1)) : qmask_t(0);
-    if (TOPS) {
-        const int n = 1 << (3 * s.top_log2);
+    if (LAY == 0) {
+        const int n = 1 << (3 * s.air_top_log2);
         for (int i = threadIdx.x; i < n; i += blockDim.x) top_s[i] = __ldg(s.air_top + i);
     }
     if (threadIdx.x == 0) {
@@ -706,7 +658,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
         live[3] = (int)Q_CHUNK;      // indices of the chunk handed out so far (exhausted: the first request draws a chunk)
     }
     __syncthreads();
-    const unsigned *top = TOPS ? top_s : s.air_top;
+    const unsigned *top = LAY == 0 ? top_s : s.air_top;
 
     for (;;) {
         // the stage with the most columns that have work
@@ -730,7 +682,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
             continue;
         }
         switch (best) {
-            case QS_MARCH: QSTAT(0, 1); q_stage_march<NST>(s, top, F, mask, lane, qp.yield_below, qp.refill_min); break;
+            case QS_MARCH: QSTAT(0, 1); q_stage_march<NST, LAY>(s, top, F, mask, lane, qp.yield_below, qp.refill_min); break;
             case QS_BLOCK:
             case QS_EXIT: q_stage_resolve<HAS_BVH>(s, F, mask, lane, best == QS_BLOCK); break;
             case QS_END: q_stage_end(s, qp.w, F, mask, live, lane); break;

@@ -14,12 +14,13 @@
 #include <unordered_map>
 #include <vector>
 
-#include "../../include/chunkycu.h"
-#include "ccu_device.cuh"
-#include "ccu_wavefront.cuh"
-#include "ccu_pool.cuh"
+#include <chrono>
+
+#include "ccu_host.h"
+#include "ccu_march.cuh"
 #include "ccu_queue.cuh"
 #include "ccu_tonemap.cuh"
+#include "ccu_layout.h"
 
 using namespace ccu;
 
@@ -43,14 +44,16 @@ __global__ void k_sun_setup(const int *sun_words, float *out /* su sv sw radius_
 
 // Thread-per-pixel path tracer: all passes of the batch in one launch, the running mean of
 // rayTracer.cl:109-112 carried in registers between passes (identical arithmetic, no memory round trip).
-template <bool WIDE>
+// MODE: 0 = the reference's own node array, 1 = commit-time layouts, 2 = commit-time layouts of a deep world.
+template <int MODE>
 __global__ void __launch_bounds__(128) k_render_mega(const __grid_constant__ DScene s, const int *__restrict__ seeds, int n_passes,
-                                                     int start_spp, float *__restrict__ res, int n_pixels) {
+                                                     int start_spp, float *res, const float *res_prev, int n_pixels) {
     for (int gid = blockIdx.x * blockDim.x + threadIdx.x; gid < n_pixels; gid += gridDim.x * blockDim.x) {
         float *px = res + (size_t)gid * 3;
-        float3 buf = f3(px[0], px[1], px[2]);
+        const float *pp = res_prev + (size_t)gid * 3;    // what the reference's single buffer holds when the window starts
+        float3 buf = f3(pp[0], pp[1], pp[2]);
         for (int pass = 0; pass < n_passes; pass++) {
-            float3 col = sample_pixel<WIDE>(s, gid, __ldg(seeds + pass));
+            float3 col = sample_pixel<MODE>(s, gid, __ldg(seeds + pass));
             int spp = start_spp + pass;
             float fs = (float)spp, fs1 = (float)(spp + 1);
             buf.x = (buf.x * fs + col.x) / fs1;
@@ -71,13 +74,17 @@ __device__ __forceinline__ int face_of(float3 n) {
     return 6;
 }
 
-// WIDE: march on the commit-time layout; the treeData index of the hit leaf (reference numbering, ClSceneLoader.java:56-59)
-// is then found by one root descent for the hit voxel only.
-template <bool WIDE>
-__global__ void __launch_bounds__(128) k_first_hit(const __grid_constant__ DScene s, int seed, int n_pixels, int *block, int *face, int *node,
+// First-hit pass (BASELINE config 2): closestIntersect (kernel.h:14-24) for the camera ray of every pixel.  Pixels are taken in
+// 32x32 screen-tile order (tile_order_pixel: neighbouring lanes walk neighbouring rays, which keeps the warp converged
+// and its brick loads in the same cache lines); with the commit-time layouts (MODE 1 / 2) the march runs on the air layout and
+// the treeData index of the hit leaf (reference numbering, ClSceneLoader.java:56-59) is found by one root descent for the hit
+// voxel only.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_first_hit(const __grid_constant__ DScene s, int seed, int n_pixels, int *block, int *face, int *node,
                                                    int *kind, float *t, float *normal, float *color) {
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n_pixels) return;
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (unsigned)n_pixels) return;
+    const int gid = tile_order_pixel(k, s.width, s.height);
     uint32_t rng = (uint32_t)seed + (uint32_t)gid;
     rng_next(rng);
     float3 o, d;
@@ -86,8 +93,8 @@ __global__ void __launch_bounds__(128) k_first_hit(const __grid_constant__ DScen
     rec.distance = inff_(); rec.material = 0; rec.surf.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
     rec.surf.color = make_float4(0, 0, 0, 0); rec.surf.emittance = 0;
     HitInfo hi = {-1, 0, 0, 0, 0};
-    bool hit = closest_intersect<WIDE>(s, o, d, rec, hi);
-    if (WIDE && hit && hi.kind == 1) {
+    bool hit = closest_intersect_mode<MODE>(s, o, d, rec, hi);
+    if (MODE != 0 && node && hit && hi.kind == 1) {
         int level;
         find_leaf(s, hi.bx, hi.by, hi.bz, level, hi.node);
     }
@@ -108,10 +115,11 @@ __global__ void __launch_bounds__(128) k_first_hit(const __grid_constant__ DScen
 }
 
 // rayTracer.cl:141-216
-template <bool WIDE>
-__global__ void __launch_bounds__(128) k_preview(const __grid_constant__ DScene s, int n_pixels, int *res) {
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n_pixels) return;
+template <int MODE>
+__global__ void __launch_bounds__(256) k_preview(const __grid_constant__ DScene s, int n_pixels, int *res) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (unsigned)n_pixels) return;
+    const int gid = tile_order_pixel(k, s.width, s.height);
     int W = s.width, H = s.height;
     int px = gid % W, py = gid / W;
     if ((px == W / 2 && (py >= H / 2 - 5 && py <= H / 2 + 5)) || (py == H / 2 && (px >= W / 2 - 5 && px <= W / 2 + 5))) {
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(128) k_preview(const __grid_constant__ DScene 
     rec.surf.color = make_float4(0, 0, 0, 0); rec.surf.emittance = 0;
     HitInfo hi = {-1, 0, 0, 0, 0};
     float3 c;
-    if (WIDE ? closest_intersect<true>(s, o, d, rec, hi) : closest_intersect<false>(s, o, d, rec, hi)) {
+    if (closest_intersect_mode<MODE>(s, o, d, rec, hi)) {
         float shading = dot3(rec.surf.normal, f3(0.25f, 0.866f, 0.433f));
         shading = fmaxf(0.3f, shading);
         c = f3(rec.surf.color.x * shading, rec.surf.color.y * shading, rec.surf.color.z * shading);
@@ -203,9 +211,10 @@ __global__ void __launch_bounds__(256) k_gather(const uint4 *__restrict__ a, uin
 // ======================================================================================================
 // host side
 // ======================================================================================================
+namespace ccu_host {
 static thread_local std::string g_err;
 
-static int fail(int code, const char *fmt, ...) {
+int fail(int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -214,127 +223,34 @@ static int fail(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
+const char *last_error() { return g_err.c_str(); }
+}  // namespace ccu_host
 
-#define CU(call)                                                                                                     \
-    do {                                                                                                             \
-        cudaError_t e_ = (call);                                                                                     \
-        if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? CCU_ENOMEM : CCU_ECUDA, "%s: %s (%s:%d)", #call, \
-                                           cudaGetErrorString(e_), __FILE__, __LINE__);                              \
-    } while (0)
-
-template <class T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    cudaError_t upload(const T *host, size_t count, cudaStream_t st) {
-        release();
-        n = count;
-        size_t alloc = std::max<size_t>(count, 4);   // zero-length arrays become a zero word (ClIntBuffer.java:15-18)
-        cudaError_t e = cudaMalloc(&p, alloc * sizeof(T));
-        if (e != cudaSuccess) { p = nullptr; return e; }
-        e = cudaMemsetAsync(p, 0, alloc * sizeof(T), st);
-        if (e != cudaSuccess) return e;
-        if (count) e = cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) return e;
-        return cudaStreamSynchronize(st);   // host memory is not retained past the call
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        n = 0;
-    }
-    size_t bytes() const { return p ? std::max<size_t>(n, 4) * sizeof(T) : 0; }
-};
-
-struct ccu_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // read-back chunks of ccu_render_merge
-    std::mutex mu;
-    int sm_count = 0;
-
-    // scene
-    DevBuf<int> tree, block_palette, quad_models, aabb_models, mat_palette, trigs, world_bvh, actor_bvh, sun_words;
-    std::vector<int> world_head, actor_head;    // first node of each BVH for the emptiness probe
-    std::vector<int> world_host, actor_host, trigs_host;   // kept for the commit-time BVH layout
-    DevBuf<int> world_rec, actor_rec, tris2;
-    int world_root = 0, actor_root = 0, use_bvh2 = 0;
-    DevBuf<uchar4> atlas, sky;
-    std::vector<int> tree_host;              // kept for the commit-time traversal layout
-    DevBuf<unsigned> top, wide;
-    DevBuf<unsigned> air_top, air_wide, air_bits;   // march-loop layout (ccu_queue.cuh)
-    int use_air = 0;
-    int cell_level = 0, top_log2 = 0, use_wide = 0;
-    int atlas_w = 0, atlas_h = 0, atlas_layers = 0;
-    int depth = 0, sky_res = 0;
-    float sky_intensity = 0;
-    int sun_host[6] = {0, 0, 0, 0, 0, 0};
-    bool have_sun = false;
-    bool committed = false;
-    DevBuf<float> sun_basis;
-    float *unorm = nullptr;
-
-    // camera
-    int projector_type = 0;
-    float cam[15] = {0};
-    DevBuf<float> rays;
-    bool have_camera = false;
-
-    // render target
-    int width = 0, height = 0;
-    float *accum = nullptr;      // running mean float[3*W*H]
-    float *pinned = nullptr;     // host staging float[3*W*H]
-    int *seeds_dev = nullptr;
-    unsigned int *work_counter = nullptr;
-    int wait_lanes = 28;
-    int refill_min = 4;
-    int exit_idle = 8;
-    int yield_below = 20;
-    int q_refill_min = 8;
-    int q_march_bias = 4;
-    int q_leaf_min = 12;
-    int q_bvh_warps = 23;
-    int q_march_warps = 22;
-    int blocks_per_sm = CCU_MIN_BLOCKS;
-    int seeds_cap = 0;
-    int window_spp = 0;
-    bool target_live = false;    // between ccu_render_begin and ccu_render_end
-    ccu_render_params params = {256, 5, 13.0f, 0};
-
-    float last_ms = 0;
-    bool timing_pending = false;
-    int64_t launches = 0;
-
-    DScene scene{};
-};
+using ccu_host::DevBuf;
+using ccu_host::DeviceGuard;
+using ccu_host::fail;
+using ccu_host::SEED_SLOTS;
+using ccu_host::SEED_SLOT_INTS;
 
 namespace {
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-    }
-    ~DeviceGuard() {
-        int cur = -1;
-        cudaGetDevice(&cur);
-        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
-    }
-};
-
-bool bvh_is_empty(const std::vector<int> &head) {   // bvh.h:23-32
-    if (head.size() < 7 || head[0] != 0) return head.size() < 7;
+bool bvh_is_empty(const std::vector<int> &bvh) {   // bvh.h:23-32
+    if (bvh.size() < 7) return true;
+    if (bvh[0] != 0) return false;
     for (int i = 1; i < 7; i++) {
         float f;
-        memcpy(&f, &head[i], 4);
+        memcpy(&f, &bvh[i], 4);
         if (!std::isnan(f)) return false;
     }
     return true;
 }
 
-int fill_scene(ccu_ctx *c) {
+int air_layout_id(const ccu_ctx *c) {   // template parameter LAY of k_render_queue
+    if (c->air_deep) return 2;
+    return (c->air_top.n <= (size_t)Q_TOP_WORDS && getenv("CCU_NO_TOPS") == nullptr) ? 0 : 1;
+}
+
+void fill_scene(ccu_ctx *c) {
     DScene &s = c->scene;
     s.tree = c->tree.p;
     s.depth = c->depth;
@@ -345,7 +261,9 @@ int fill_scene(ccu_ctx *c) {
     s.use_wide = c->use_wide;
     s.air_top = c->air_top.p;
     s.air_wide = c->air_wide.p;
-    s.air_bits = c->air_bits.p;
+    s.air_bricks = c->air_bricks.p;
+    s.air_cell_level = c->air_cell_level;
+    s.air_top_log2 = c->air_top_log2;
     s.world_rec = reinterpret_cast<const int4 *>(c->world_rec.p);
     s.actor_rec = reinterpret_cast<const int4 *>(c->actor_rec.p);
     s.tris2 = reinterpret_cast<const int4 *>(c->tris2.p);
@@ -359,8 +277,9 @@ int fill_scene(ccu_ctx *c) {
     s.world_bvh = c->world_bvh.p;
     s.actor_bvh = c->actor_bvh.p;
     s.trigs = c->trigs.p;
-    s.world_bvh_empty = bvh_is_empty(c->world_head);
-    s.actor_bvh_empty = bvh_is_empty(c->actor_head);
+    const bool no_entities = (c->params.flags & CCU_RENDER_NO_ENTITIES) != 0;
+    s.world_bvh_empty = no_entities || bvh_is_empty(c->world_host);
+    s.actor_bvh_empty = no_entities || bvh_is_empty(c->actor_host);
     s.atlas = c->atlas.p;
     s.atlas_w = c->atlas_w; s.atlas_h = c->atlas_h; s.atlas_layers = c->atlas_layers;
     s.atlas_tiles_x = (c->atlas_w + 15) / 16; s.atlas_tiles_y = (c->atlas_h + 15) / 16;
@@ -369,29 +288,34 @@ int fill_scene(ccu_ctx *c) {
     s.sky_intensity = c->sky_intensity;
     s.unorm = c->unorm;
     s.sun_flags = c->sun_host[0]; s.sun_tex_size = c->sun_host[1]; s.sun_tex = c->sun_host[2];
+    if (c->params.flags & CCU_RENDER_NO_SUN) s.sun_flags &= ~1;
     memcpy(&s.sun_intensity, &c->sun_host[3], 4);
     s.projector_type = c->projector_type;
     memcpy(s.cam, c->cam, sizeof s.cam);
-    s.rays = c->rays.p;
+    s.rays = c->rays[c->rays_active].p;
     s.width = c->width; s.height = c->height;
     if (c->height > 0) {
         s.half_width = (float)(c->width / (2.0 * c->height));   // rayTracer.cl:66
         s.inv_height = (float)(1.0 / c->height);                // rayTracer.cl:67
     }
     s.draw_depth = c->params.draw_depth; s.max_depth = c->params.max_depth; s.emitter_scale = c->params.emitter_scale;
-    return CCU_OK;
 }
 
-int upload_words(ccu_ctx *c, DevBuf<int> &dst, const int32_t *words, int64_t n, const char *what) {
+// Upload one of the reference's packed int arrays; `after` runs under the context lock once the upload succeeded
+// (host-side copies and flags change together with the device buffer).
+template <class F>
+int upload_words(ccu_ctx *c, DevBuf<int> ccu_ctx::*dst, const int32_t *words, int64_t n, const char *what, F after) {
     if (!c) return fail(CCU_EINVAL, "%s: null context", what);
     if (n < 0 || (n > 0 && !words)) return fail(CCU_EINVAL, "%s: bad array (n=%lld)", what, (long long)n);
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     c->committed = false;
-    CU(dst.upload(words, (size_t)n, c->stream));
+    CU((c->*dst).upload(words, (size_t)n, c->stream));
+    after();
     return CCU_OK;
 }
 
+// device time of the last render / first-hit / preview / tonemap launch(es); waits for them (caller holds c->mu)
 void stop_timer(ccu_ctx *c) {
     if (c->timing_pending) {
         cudaEventSynchronize(c->ev1);
@@ -400,225 +324,140 @@ void stop_timer(ccu_ctx *c) {
     }
 }
 
+// waits for everything queued on the render stream WITHOUT holding the context lock
+int wait_render_stream(ccu_ctx *c) {
+    cudaEvent_t ev = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        DeviceGuard g(c->device);
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e = cudaEventRecord(ev, c->stream);
+        if (e != cudaSuccess) { cudaEventDestroy(ev); return fail(CCU_ECUDA, "cudaEventRecord: %s", cudaGetErrorString(e)); }
+    }
+    cudaError_t e = cudaEventSynchronize(ev);
+    cudaEventDestroy(ev);
+    if (e != cudaSuccess) return fail(CCU_ECUDA, "render stream: %s", cudaGetErrorString(e));
+    return CCU_OK;
+}
+
+int join_merge_locked(ccu_ctx *c, std::unique_lock<std::mutex> &lk) {
+    if (!c->merge.active) return CCU_OK;
+    std::thread t = std::move(c->merge.worker);
+    lk.unlock();
+    if (t.joinable()) t.join();
+    lk.lock();
+    c->merge.active = false;
+    if (c->merge.status != CCU_OK) {
+        const int rc = c->merge.status;
+        c->merge.status = CCU_OK;
+        return fail(rc, "%s", c->merge.error.c_str());
+    }
+    return CCU_OK;
+}
+
+void free_target(ccu_ctx *c) {
+    for (int i = 0; i < 2; i++) {
+        if (c->accum[i]) cudaFree(c->accum[i]);
+        c->accum[i] = nullptr;
+    }
+    if (c->pinned) cudaFreeHost(c->pinned);
+    c->pinned = nullptr;
+    c->accum_floats = 0;
+}
+
+template <class K>
+cudaError_t allow_smem(K kernel, int bytes) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+
 }  // namespace
 
+namespace ccu_host {
 
-// ------------------------------------------------------------------------------------------------------
-// commit-time traversal layout (see DScene::top / DScene::wide)
-// ------------------------------------------------------------------------------------------------------
-namespace {
-struct WideLayout {
-    std::vector<unsigned> top, wide;
-    int cell_level = 0, top_log2 = 0;
-    bool ok = true;
-};
-
-inline unsigned wide_leaf(int word, int level, bool &ok) {
-    long long v = -(long long)word;
-    unsigned val;
-    if (v == 0x7FFFFFFELL) val = CCU_WIDE_ANY;
-    else if (v >= 0 && v < (long long)CCU_WIDE_ANY) val = (unsigned)v;
-    else { ok = false; val = 0; }
-    return CCU_WIDE_LEAF | ((unsigned)level << 26) | val;
-}
-
-unsigned wide_node(const int *tree, size_t n, int word, int lvl, WideLayout &b) {
-    if (lvl < 2 || (size_t)word + 7 >= n) { b.ok = false; return wide_leaf(0, 0, b.ok); }
-    const size_t idx = b.wide.size() / 64;
-    if (idx >= 0x7FFFFFFFu) { b.ok = false; return wide_leaf(0, 0, b.ok); }
-    b.wide.resize(b.wide.size() + 64);
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++)
-            for (int k = 0; k < 4; k++) {
-                unsigned e;
-                int c1 = tree[(size_t)word + ((((i >> 1) & 1) << 2) | (((j >> 1) & 1) << 1) | ((k >> 1) & 1))];
-                if (c1 <= 0) {
-                    e = wide_leaf(c1, lvl - 1, b.ok);
-                } else if ((size_t)c1 + 7 >= n) {
-                    b.ok = false;
-                    e = wide_leaf(0, 0, b.ok);
-                } else {
-                    int c2 = tree[(size_t)c1 + (((i & 1) << 2) | ((j & 1) << 1) | (k & 1))];
-                    e = c2 <= 0 ? wide_leaf(c2, lvl - 2, b.ok) : wide_node(tree, n, c2, lvl - 2, b);
-                }
-                b.wide[idx * 64 + ((i << 4) | (j << 2) | k)] = e;
-            }
-    return (unsigned)idx;
-}
-
-// "Air layout" for the march loop (ccu_queue.cuh lean_probe): the same top table / 64-ary nodes, but an entry only says
-// air or not (bit 0 = 1: not air) plus the leaf level, and the finest nodes (4^3 voxels) shrink from 64 words to a
-// 128-bit map of 2-bit codes (0 = not air, 1 = air leaf of level 0, 2 = air leaf of level 1).  The march loop needs
-// nothing else (octree.h:89-106: an air leaf is left through its cube, anything else goes to the block test), and the
-// structure is ~10x smaller than the value-carrying layout, which is what keeps it in L1.
-struct AirLayout {
-    std::vector<unsigned> top, wide, bits;
-    bool ok = true;
-};
-
-inline unsigned air_leaf(int word, int level) { return CCU_WIDE_LEAF | ((unsigned)level << 26) | (word == 0 ? 0u : 1u); }
-
-unsigned air_node(const int *tree, size_t n, int word, int lvl, AirLayout &b) {
-    if (lvl < 2 || (size_t)word + 7 >= n) { b.ok = false; return air_leaf(1, 0); }
-    if (lvl == 2) {
-        const size_t idx = b.bits.size() / 4;
-        if (idx >= 0x7FFFFFFFu) { b.ok = false; return air_leaf(1, 0); }
-        b.bits.resize(b.bits.size() + 4, 0u);
-        for (int i = 0; i < 4; i++)
-            for (int j = 0; j < 4; j++)
-                for (int k = 0; k < 4; k++) {
-                    unsigned code;
-                    int c1 = tree[(size_t)word + ((((i >> 1) & 1) << 2) | (((j >> 1) & 1) << 1) | ((k >> 1) & 1))];
-                    if (c1 <= 0) {
-                        code = c1 == 0 ? 2u : 0u;
-                    } else if ((size_t)c1 + 7 >= n) {
-                        b.ok = false;
-                        code = 0;
-                    } else {
-                        int c2 = tree[(size_t)c1 + (((i & 1) << 2) | ((j & 1) << 1) | (k & 1))];
-                        if (c2 > 0) b.ok = false;          // deeper than the declared depth
-                        code = c2 == 0 ? 1u : 0u;
-                    }
-                    const int v = (i << 4) | (j << 2) | k;
-                    b.bits[idx * 4 + (v >> 4)] |= code << ((v & 15) * 2);
-                }
-        return (unsigned)idx;
+// Read floats [lo, hi) of `src_dev` (a finished window's running mean) back through the pinned staging buffer in chunks on
+// `st` and fold each chunk into the host sample buffer as it lands (OpenClPathTracingRenderer.java:164-173):
+//   sample[i] = (sample[i] * ds + mean[i] * dp) * sinv
+int merge_window_range(ccu_ctx *c, const float *src_dev, size_t lo, size_t hi, double *sample_buffer, double ds, double dp, double sinv,
+                       cudaStream_t st, unsigned max_threads) {
+    if (hi <= lo) return CCU_OK;
+    constexpr int NCH = 8;
+    const size_t n = hi - lo;
+    const size_t chunk = ((n + NCH - 1) / NCH + 63) & ~(size_t)63;
+    for (int k = 0; k < NCH; k++) {
+        const size_t a = lo + std::min(n, k * chunk), b = lo + std::min(n, (k + 1) * chunk);
+        if (b > a) CU(cudaMemcpyAsync(c->pinned + a, src_dev + a, (b - a) * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(c->chunk_ev[k], st));
     }
-    const size_t idx = b.wide.size() / 64;
-    if (idx >= 0x7FFFFFFFu) { b.ok = false; return air_leaf(1, 0); }
-    b.wide.resize(b.wide.size() + 64);
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++)
-            for (int k = 0; k < 4; k++) {
-                unsigned e;
-                int c1 = tree[(size_t)word + ((((i >> 1) & 1) << 2) | (((j >> 1) & 1) << 1) | ((k >> 1) & 1))];
-                if (c1 <= 0) {
-                    e = air_leaf(c1, lvl - 1);
-                } else if ((size_t)c1 + 7 >= n) {
-                    b.ok = false;
-                    e = air_leaf(1, 0);
-                } else {
-                    int c2 = tree[(size_t)c1 + (((i & 1) << 2) | ((j & 1) << 1) | (k & 1))];
-                    e = c2 <= 0 ? air_leaf(c2, lvl - 2) : air_node(tree, n, c2, lvl - 2, b);
-                }
-                b.wide[idx * 64 + ((i << 4) | (j << 2) | k)] = e;
-            }
-    return (unsigned)idx;
-}
-
-// same cell level / table shape as the wide layout
-AirLayout build_air_layout(const int *tree, size_t n, int depth, int cl) {
-    AirLayout b;
-    const int dim = 1 << (depth - cl);
-    b.top.assign((size_t)dim * dim * dim, 0u);
-    for (int x = 0; x < dim && b.ok; x++)
-        for (int y = 0; y < dim; y++)
-            for (int z = 0; z < dim; z++) {
-                int level = depth;
-                int word = tree[0];
-                while (word > 0 && level > cl) {
-                    level--;
-                    int sh = level - cl;
-                    size_t at = (size_t)word + ((((x >> sh) & 1) << 2) | (((y >> sh) & 1) << 1) | ((z >> sh) & 1));
-                    if (at >= n) { b.ok = false; word = 0; break; }
-                    word = tree[at];
-                }
-                if (word > 0 && cl < 2) { b.ok = false; word = -1; }
-                b.top[((size_t)x * dim + y) * dim + z] = word <= 0 ? air_leaf(word, level) : air_node(tree, n, word, cl, b);
-            }
-    if (b.wide.empty()) b.wide.assign(64, air_leaf(1, 0));
-    if (b.bits.empty()) b.bits.assign(4, 0u);
-    return b;
-}
-
-// Traversal layout of a packed BVH (PackedBvhNode.java:22-31: 7 ints per node, first child at node + 7, second child at
-// node[0]) for the BVH stage of ccu_queue.cuh: one 64-byte record per inner node holding BOTH children's boxes
-// (bvh.h:73-91 fetches exactly those at every inner node) and a reference per child, and 16-byte aligned triangle
-// blocks.  ref >= 0: record index; ref < 0: leaf, -(1 + offset of its block in `tris`, in units of 4 words).
-struct BvhLayout {
-    std::vector<int> rec;
-    int root = 0;
-    bool ok = true;
-};
-struct TriRepack {
-    std::vector<int> tris;                       // per leaf: {count, 0, 0, 0} + count x 20 words (PackedTriangle.java:46-78)
-    int add(const std::vector<int> &trigs, int prim, bool &ok) {
-        if (prim < 0 || (size_t)prim >= trigs.size()) { ok = false; return 0; }
-        const int count = trigs[(size_t)prim];
-        if (count < 0 || (size_t)prim + 1 + (size_t)count * 20 > trigs.size()) { ok = false; return 0; }
-        const int off = (int)(tris.size() / 4);
-        tris.push_back(count); tris.push_back(0); tris.push_back(0); tris.push_back(0);
-        tris.insert(tris.end(), trigs.begin() + prim + 1, trigs.begin() + prim + 1 + (size_t)count * 20);
-        return off;
-    }
-};
-
-int bvh_ref(const std::vector<int> &bvh, const std::vector<int> &trigs, size_t node, int depth, BvhLayout &b, TriRepack &tr,
-            std::unordered_map<int, int> &leaf_map) {
-    if (!b.ok) return -1;
-    // deeper than the traversal stack of the reference (int nodesToVisit[64], bvh.h:38): undefined there, refused here
-    if (node + 6 >= bvh.size() || depth >= 64) { b.ok = false; return -1; }
-    const int head = bvh[node];
-    if (head <= 0) {
-        const int prim = -head;
-        auto it = leaf_map.find(prim);   // a leaf block referenced twice (both BVHs share the palette) is stored once
-        int off;
-        if (it != leaf_map.end()) {
-            off = it->second;
-        } else {
-            off = tr.add(trigs, prim, b.ok);
-            leaf_map.emplace(prim, off);
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned nt = std::max(1u, std::min(std::min(16u, max_threads), hw ? hw : 4u));
+    if (n < (1u << 20)) nt = 1;
+    const float *src = c->pinned;
+    cudaEvent_t *evs = c->chunk_ev;
+    const int device = c->device;
+    auto work = [=](unsigned t) {
+        cudaSetDevice(device);
+        for (int k = 0; k < NCH; k++) {
+            const size_t a = lo + std::min(n, k * chunk), b = lo + std::min(n, (k + 1) * chunk);
+            cudaEventSynchronize(evs[k]);
+            const size_t len = b - a, part = (len + nt - 1) / nt;
+            const size_t i0 = a + std::min(len, t * part), i1 = a + std::min(len, (t + 1) * part);
+            for (size_t i = i0; i < i1; i++) sample_buffer[i] = (sample_buffer[i] * ds + (double)src[i] * dp) * sinv;
         }
-        return -(1 + off);
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto &t : th) t.join();
     }
-    const size_t left = node + 7, right = (size_t)head;
-    if (left + 6 >= bvh.size() || right + 6 >= bvh.size()) { b.ok = false; return -1; }
-    const size_t r = b.rec.size() / 16;
-    b.rec.resize(b.rec.size() + 16, 0);
-    for (int i = 0; i < 6; i++) {
-        b.rec[r * 16 + i] = bvh[left + 1 + i];
-        b.rec[r * 16 + 6 + i] = bvh[right + 1 + i];
-    }
-    const int rl = bvh_ref(bvh, trigs, left, depth + 1, b, tr, leaf_map);
-    const int rr = bvh_ref(bvh, trigs, right, depth + 1, b, tr, leaf_map);
-    b.rec[r * 16 + 12] = rl;
-    b.rec[r * 16 + 13] = rr;
-    return (int)r;
+    CU(cudaStreamSynchronize(st));
+    return CCU_OK;
 }
 
-WideLayout build_wide_layout(const int *tree, size_t n, int depth) {
-    WideLayout b;
-    int cl = std::max(depth - 7, 4);
-    if (const char *e = getenv("CCU_CELL_LEVEL")) cl = std::max(0, atoi(e));   // tuning knob: level of the top table's cells
-    if (cl & 1) cl++;
-    if (cl > depth) cl = depth & ~1;
-    b.cell_level = cl;
-    b.top_log2 = depth - cl;
-    const int dim = 1 << b.top_log2;
-    b.top.assign((size_t)dim * dim * dim, 0u);
-    for (int x = 0; x < dim && b.ok; x++)
-        for (int y = 0; y < dim; y++)
-            for (int z = 0; z < dim; z++) {
-                int level = depth;
-                int word = tree[0];
-                while (word > 0 && level > cl) {
-                    level--;
-                    int sh = level - cl;
-                    size_t at = (size_t)word + ((((x >> sh) & 1) << 2) | (((y >> sh) & 1) << 1) | ((z >> sh) & 1));
-                    if (at >= n) { b.ok = false; word = 0; break; }
-                    word = tree[at];
-                }
-                b.top[((size_t)x * dim + y) * dim + z] = word <= 0 ? wide_leaf(word, level, b.ok) : wide_node(tree, n, word, cl, b);
-            }
-    if (b.wide.empty()) b.wide.assign(64, wide_leaf(0, 0, b.ok));
-    return b;
+template <class T>
+static int copy_buf(ccu_ctx *src, ccu_ctx *dst, DevBuf<T> ccu_ctx::*member) {
+    DevBuf<T> &a = src->*member, &b = dst->*member;
+    if (!a.p) { b.release(); return CCU_OK; }
+    CU(b.alloc(a.n));
+    CU(cudaMemcpyPeerAsync(b.p, dst->device, a.p, src->device, a.bytes(), dst->stream));
+    return CCU_OK;
 }
-}  // namespace
+
+// Copy the committed scene of `src` (uploaded arrays and commit-time layouts) to `dst` device-to-device.
+int replicate_scene(ccu_ctx *src, ccu_ctx *dst) {
+    if (src == dst) return CCU_OK;
+    std::lock(src->mu, dst->mu);
+    std::lock_guard<std::mutex> l1(src->mu, std::adopt_lock), l2(dst->mu, std::adopt_lock);
+    if (!src->committed) return fail(CCU_ESTATE, "replicate: source scene not committed");
+    DeviceGuard g(dst->device);
+    cudaStreamSynchronize(dst->stream);
+    int rc = CCU_OK;
+#define CP(m) if (rc == CCU_OK) rc = copy_buf(src, dst, &ccu_ctx::m)
+    CP(tree); CP(block_palette); CP(quad_models); CP(aabb_models); CP(mat_palette); CP(trigs); CP(world_bvh); CP(actor_bvh); CP(sun_words);
+    CP(top); CP(wide); CP(air_top); CP(air_wide); CP(air_bricks); CP(world_rec); CP(actor_rec); CP(tris2); CP(cube_rec); CP(atlas); CP(sky); CP(sun_basis);
+#undef CP
+    if (rc != CCU_OK) return rc;
+    dst->world_host = src->world_host.size() >= 7 ? std::vector<int>(src->world_host.begin(), src->world_host.begin() + 7) : src->world_host;
+    dst->actor_host = src->actor_host.size() >= 7 ? std::vector<int>(src->actor_host.begin(), src->actor_host.begin() + 7) : src->actor_host;
+    dst->tree_host.clear(); dst->trigs_host.clear(); dst->block_host.clear(); dst->mat_host.clear();
+    dst->world_root = src->world_root; dst->actor_root = src->actor_root; dst->use_bvh2 = src->use_bvh2; dst->use_air = src->use_air;
+    dst->air_deep = src->air_deep; dst->cell_level = src->cell_level; dst->top_log2 = src->top_log2; dst->use_wide = src->use_wide;
+    dst->air_cell_level = src->air_cell_level; dst->air_top_log2 = src->air_top_log2;
+    dst->atlas_w = src->atlas_w; dst->atlas_h = src->atlas_h; dst->atlas_layers = src->atlas_layers;
+    dst->depth = src->depth; dst->sky_res = src->sky_res; dst->sky_intensity = src->sky_intensity;
+    memcpy(dst->sun_host, src->sun_host, sizeof dst->sun_host);
+    dst->have_sun = dst->have_octree = dst->have_blocks = dst->have_mats = dst->have_atlas = dst->have_sky = true;
+    dst->scene.su = src->scene.su; dst->scene.sv = src->scene.sv; dst->scene.sw = src->scene.sw; dst->scene.sun_radius_cos = src->scene.sun_radius_cos;
+    CU(cudaStreamSynchronize(dst->stream));
+    dst->committed = true;
+    return CCU_OK;
+}
+
+}  // namespace ccu_host
 
 extern "C" {
 
-const char *ccu_last_error(void) { return g_err.c_str(); }
-const char *ccu_version(void) { return "chunkycu 0.1 (sm_100a)"; }
+const char *ccu_last_error(void) { return ccu_host::last_error(); }
+const char *ccu_version(void) { return "chunkycu 0.2 (sm_100a)"; }
 
 int ccu_device_count(int *count) {
     if (!count) return fail(CCU_EINVAL, "ccu_device_count: null");
@@ -664,28 +503,26 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     ccu_ctx *c = new ccu_ctx();
     c->device = device_index;
     c->sm_count = p.multiProcessorCount;
-    if (const char *e = getenv("CCU_WAIT_LANES")) c->wait_lanes = std::max(1, std::min(32, atoi(e)));
-    if (const char *e = getenv("CCU_REFILL_MIN")) c->refill_min = std::max(1, std::min(32, atoi(e)));
-    if (const char *e = getenv("CCU_EXIT_IDLE")) c->exit_idle = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_Q_MARCH_WARPS")) c->q_march_warps = std::max(1, std::min(64, atoi(e)));
     if (const char *e = getenv("CCU_Q_BVH_WARPS")) c->q_bvh_warps = std::max(1, std::min(64, atoi(e)));
     if (const char *e = getenv("CCU_Q_LEAF_MIN")) c->q_leaf_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_Q_MARCH_BIAS")) c->q_march_bias = std::max(-32, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_Q_REFILL_MIN")) c->q_refill_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_YIELD_BELOW")) c->yield_below = std::max(0, std::min(33, atoi(e)));
-    if (const char *e = getenv("CCU_BLOCKS_PER_SM")) c->blocks_per_sm = std::max(1, std::min(8, atoi(e)));
     DeviceGuard g(device_index);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_pool<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, q_smem_bytes(true, true));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, q_smem_bytes(false, true));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, q_smem_bytes(true, false));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render_queue<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, q_smem_bytes(false, false));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->window_ev, cudaEventDisableTiming);
+    for (int k = 0; k < 8 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&c->rays_used[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = allow_smem(k_render_queue<false, 0>, q_smem_bytes(false, true));
+    if (e == cudaSuccess) e = allow_smem(k_render_queue<false, 1>, q_smem_bytes(false, false));
+    if (e == cudaSuccess) e = allow_smem(k_render_queue<false, 2>, q_smem_bytes(false, false));
+    if (e == cudaSuccess) e = allow_smem(k_render_queue<true, 0>, q_smem_bytes(true, true));
+    if (e == cudaSuccess) e = allow_smem(k_render_queue<true, 1>, q_smem_bytes(true, false));
+    if (e == cudaSuccess) e = allow_smem(k_render_queue<true, 2>, q_smem_bytes(true, false));
     if (e == cudaSuccess) e = cudaMalloc(&c->unorm, 256 * sizeof(float));
     if (e == cudaSuccess) {
         k_unorm_table<<<1, 256, 0, c->stream>>>(c->unorm);
@@ -700,66 +537,81 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     return CCU_OK;
 }
 
-int ccu_render_end(ccu_ctx *c);
-
 int ccu_ctx_destroy(ccu_ctx *c) {
     if (!c) return CCU_OK;
     {
-        std::lock_guard<std::mutex> lk(c->mu);
+        std::unique_lock<std::mutex> lk(c->mu);
+        join_merge_locked(c, lk);
         DeviceGuard g(c->device);
         cudaStreamSynchronize(c->stream);
-        c->tree.release(); c->top.release(); c->wide.release(); c->air_top.release(); c->air_wide.release(); c->air_bits.release(); c->world_rec.release(); c->actor_rec.release(); c->tris2.release(); c->block_palette.release(); c->quad_models.release(); c->aabb_models.release();
-        c->mat_palette.release(); c->trigs.release(); c->world_bvh.release(); c->actor_bvh.release();
-        c->sun_words.release(); c->atlas.release(); c->sky.release(); c->rays.release(); c->sun_basis.release();
-        if (c->accum) cudaFree(c->accum);
-        if (c->pinned) cudaFreeHost(c->pinned);
+        cudaStreamSynchronize(c->copy_stream);
+        c->tree.release(); c->top.release(); c->wide.release(); c->air_top.release(); c->air_wide.release(); c->air_bricks.release();
+        c->world_rec.release(); c->actor_rec.release(); c->tris2.release(); c->cube_rec.release(); c->block_palette.release();
+        c->quad_models.release(); c->aabb_models.release(); c->mat_palette.release(); c->trigs.release(); c->world_bvh.release();
+        c->actor_bvh.release(); c->sun_words.release(); c->atlas.release(); c->sky.release(); c->rays[0].release(); c->rays[1].release();
+        c->sun_basis.release();
+        free_target(c);
         if (c->seeds_dev) cudaFree(c->seeds_dev);
+        if (c->seeds_pinned) cudaFreeHost(c->seeds_pinned);
+        for (auto &e : c->seeds_ev) if (e) cudaEventDestroy(e);
+        if (c->fh_scratch) cudaFree(c->fh_scratch);
         if (c->work_counter) cudaFree(c->work_counter);
         if (c->unorm) cudaFree(c->unorm);
         for (auto &e : c->chunk_ev) if (e) cudaEventDestroy(e);
+        for (auto &e : c->rays_used) if (e) cudaEventDestroy(e);
+        if (c->window_ev) cudaEventDestroy(c->window_ev);
         cudaEventDestroy(c->ev0);
         cudaEventDestroy(c->ev1);
+        cudaStreamDestroy(c->copy_stream);
         cudaStreamDestroy(c->stream);
     }
     delete c;
     return CCU_OK;
 }
 
+// A new scene starts from nothing, as the reference's loader does (fresh palettes and EMPTY_NODE BVHs on every load,
+// AbstractSceneLoader.java:70-140): arrays of the previous scene do not leak into a scene that does not set them.
 int ccu_scene_begin(ccu_ctx *c) {
     if (!c) return fail(CCU_EINVAL, "ccu_scene_begin: null context");
     std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
     c->committed = false;
+    c->quad_models.release(); c->aabb_models.release(); c->trigs.release(); c->world_bvh.release(); c->actor_bvh.release();
+    c->world_host.clear(); c->actor_host.clear(); c->trigs_host.clear();
+    c->have_octree = c->have_blocks = c->have_mats = c->have_atlas = c->have_sky = c->have_sun = false;
     return CCU_OK;
 }
 
 int ccu_scene_set_octree(ccu_ctx *c, const int32_t *tree, int64_t n, int32_t depth) {
     if (depth < 0 || depth > 30) return fail(CCU_EINVAL, "octree depth %d out of range", depth);
     if (n < 1) return fail(CCU_EINVAL, "octree needs at least the root word");
-    int rc = upload_words(c, c->tree, tree, n, "ccu_scene_set_octree");
-    if (rc == CCU_OK) {
+    return upload_words(c, &ccu_ctx::tree, tree, n, "ccu_scene_set_octree", [&] {
         c->depth = depth;
         c->tree_host.assign(tree, tree + n);
-    }
-    return rc;
+        c->have_octree = true;
+    });
 }
-int ccu_scene_set_block_palette(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->block_palette, w, n, "ccu_scene_set_block_palette"); }
-int ccu_scene_set_quad_models(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->quad_models, w, n, "ccu_scene_set_quad_models"); }
-int ccu_scene_set_aabb_models(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->aabb_models, w, n, "ccu_scene_set_aabb_models"); }
-int ccu_scene_set_material_palette(ccu_ctx *c, const int32_t *w, int64_t n) { return upload_words(c, c->mat_palette, w, n, "ccu_scene_set_material_palette"); }
+int ccu_scene_set_block_palette(ccu_ctx *c, const int32_t *w, int64_t n) {
+    return upload_words(c, &ccu_ctx::block_palette, w, n, "ccu_scene_set_block_palette", [&] { c->block_host.assign(w, w + n); c->have_blocks = true; });
+}
+int ccu_scene_set_quad_models(ccu_ctx *c, const int32_t *w, int64_t n) {
+    return upload_words(c, &ccu_ctx::quad_models, w, n, "ccu_scene_set_quad_models", [] {});
+}
+int ccu_scene_set_aabb_models(ccu_ctx *c, const int32_t *w, int64_t n) {
+    return upload_words(c, &ccu_ctx::aabb_models, w, n, "ccu_scene_set_aabb_models", [] {});
+}
+int ccu_scene_set_material_palette(ccu_ctx *c, const int32_t *w, int64_t n) {
+    return upload_words(c, &ccu_ctx::mat_palette, w, n, "ccu_scene_set_material_palette", [&] { c->mat_host.assign(w, w + n); c->have_mats = true; });
+}
 int ccu_scene_set_triangles(ccu_ctx *c, const int32_t *w, int64_t n) {
-    int rc = upload_words(c, c->trigs, w, n, "ccu_scene_set_triangles");
-    if (rc == CCU_OK) c->trigs_host.assign(w, w + n);
-    return rc;
+    return upload_words(c, &ccu_ctx::trigs, w, n, "ccu_scene_set_triangles", [&] { c->trigs_host.assign(w, w + n); });
 }
 int ccu_scene_set_world_bvh(ccu_ctx *c, const int32_t *w, int64_t n) {
-    int rc = upload_words(c, c->world_bvh, w, n, "ccu_scene_set_world_bvh");
-    if (rc == CCU_OK) { c->world_head.assign(w, w + std::min<int64_t>(n, 7)); c->world_host.assign(w, w + n); }
-    return rc;
+    return upload_words(c, &ccu_ctx::world_bvh, w, n, "ccu_scene_set_world_bvh", [&] { c->world_host.assign(w, w + n); });
 }
 int ccu_scene_set_actor_bvh(ccu_ctx *c, const int32_t *w, int64_t n) {
-    int rc = upload_words(c, c->actor_bvh, w, n, "ccu_scene_set_actor_bvh");
-    if (rc == CCU_OK) { c->actor_head.assign(w, w + std::min<int64_t>(n, 7)); c->actor_host.assign(w, w + n); }
-    return rc;
+    return upload_words(c, &ccu_ctx::actor_bvh, w, n, "ccu_scene_set_actor_bvh", [&] { c->actor_host.assign(w, w + n); });
 }
 
 int ccu_scene_atlas_create(ccu_ctx *c, int32_t width, int32_t height, int32_t layers) {
@@ -768,19 +620,19 @@ int ccu_scene_atlas_create(ccu_ctx *c, int32_t width, int32_t height, int32_t la
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     c->committed = false;
-    c->atlas.release();
-    size_t tiles = (size_t)((width + 15) / 16) * ((height + 15) / 16) * layers;
-    c->atlas.n = tiles * 256;
-    CU(cudaMalloc(&c->atlas.p, c->atlas.n * sizeof(uchar4)));
+    c->have_atlas = false;
+    const size_t tiles = (size_t)((width + 15) / 16) * ((height + 15) / 16) * layers;
+    CU(c->atlas.alloc(tiles * 256));
     CU(cudaMemsetAsync(c->atlas.p, 0, c->atlas.n * sizeof(uchar4), c->stream));
     c->atlas_w = width; c->atlas_h = height; c->atlas_layers = layers;
+    c->have_atlas = true;
     return CCU_OK;
 }
 
 int ccu_scene_atlas_write(ccu_ctx *c, int32_t x, int32_t y, int32_t layer, int32_t w, int32_t h, const uint8_t *rgba) {
     if (!c) return fail(CCU_EINVAL, "ccu_scene_atlas_write: null context");
     std::lock_guard<std::mutex> lk(c->mu);
-    if (!c->atlas.p) return fail(CCU_ESTATE, "atlas not created");
+    if (!c->atlas.p || !c->have_atlas) return fail(CCU_ESTATE, "atlas not created");
     if (!rgba || w <= 0 || h <= 0 || x < 0 || y < 0 || layer < 0 || x + w > c->atlas_w || y + h > c->atlas_h || layer >= c->atlas_layers)
         return fail(CCU_EINVAL, "atlas write %dx%d at (%d,%d,%d) outside %dx%dx%d", w, h, x, y, layer, c->atlas_w, c->atlas_h, c->atlas_layers);
     DeviceGuard g(c->device);
@@ -820,6 +672,7 @@ int ccu_scene_set_sky(ccu_ctx *c, const uint8_t *rgba, int32_t res, float sky_in
     CU(c->sky.upload(reinterpret_cast<const uchar4 *>(rgba), (size_t)res * res, c->stream));
     c->sky_res = res;
     c->sky_intensity = sky_intensity;
+    c->have_sky = true;
     return CCU_OK;
 }
 
@@ -837,22 +690,22 @@ int ccu_scene_set_sun(ccu_ctx *c, const int32_t sun_words[6]) {
 int ccu_scene_commit(ccu_ctx *c) {
     if (!c) return fail(CCU_EINVAL, "ccu_scene_commit: null context");
     std::lock_guard<std::mutex> lk(c->mu);
-    if (!c->tree.p) return fail(CCU_ESTATE, "commit: octree not set");
-    if (!c->block_palette.p || !c->mat_palette.p) return fail(CCU_ESTATE, "commit: block/material palette not set");
-    if (!c->atlas.p) return fail(CCU_ESTATE, "commit: texture atlas not set");
-    if (!c->sky.p) return fail(CCU_ESTATE, "commit: sky not set");
+    if (!c->tree.p || !c->have_octree) return fail(CCU_ESTATE, "commit: octree not set");
+    if (!c->have_blocks || !c->have_mats) return fail(CCU_ESTATE, "commit: block/material palette not set");
+    if (!c->have_atlas) return fail(CCU_ESTATE, "commit: texture atlas not set");
+    if (!c->have_sky) return fail(CCU_ESTATE, "commit: sky not set");
     if (!c->have_sun) return fail(CCU_ESTATE, "commit: sun not set");
     DeviceGuard g(c->device);
-    // absent optional palettes behave as the reference's single zero word
+    const auto t0 = std::chrono::steady_clock::now();
+    // absent optional palettes behave as the reference's single zero word / EMPTY_NODE
     int zero = 0;
     if (!c->quad_models.p) CU(c->quad_models.upload(&zero, 0, c->stream));
     if (!c->aabb_models.p) CU(c->aabb_models.upload(&zero, 0, c->stream));
-    if (!c->trigs.p) CU(c->trigs.upload(&zero, 0, c->stream));
-    if (!c->trigs.p || c->trigs.n == 0) c->trigs_host.clear();
-    if (!c->world_bvh.p) { CU(c->world_bvh.upload(&zero, 0, c->stream)); c->world_head.clear(); c->world_host.clear(); }
-    if (!c->actor_bvh.p) { CU(c->actor_bvh.upload(&zero, 0, c->stream)); c->actor_head.clear(); c->actor_host.clear(); }
-    // traversal layout: dense top table + 64-ary nodes (two octree levels per load); falls back to the plain
-    // reference layout if a leaf value cannot be encoded
+    if (!c->trigs.p) { CU(c->trigs.upload(&zero, 0, c->stream)); c->trigs_host.clear(); }
+    if (!c->world_bvh.p) { CU(c->world_bvh.upload(&zero, 0, c->stream)); c->world_host.clear(); }
+    if (!c->actor_bvh.p) { CU(c->actor_bvh.upload(&zero, 0, c->stream)); c->actor_host.clear(); }
+    // octree layouts: value-carrying (top table + 64-ary nodes) and march layout (top table + bricks); a tree that cannot be
+    // encoded (malformed, leaf values beyond 26 bits) leaves the flags at 0 and rendering uses the reference's own array
     {
         const bool enable = getenv("CCU_NO_WIDE") == nullptr;
         WideLayout wl = build_wide_layout(c->tree_host.data(), c->tree_host.size(), c->depth);
@@ -861,28 +714,31 @@ int ccu_scene_commit(ccu_ctx *c) {
         c->top_log2 = wl.top_log2;
         CU(c->top.upload(wl.top.data(), wl.top.size(), c->stream));
         CU(c->wide.upload(wl.wide.data(), wl.wide.size(), c->stream));
-        AirLayout al = build_air_layout(c->tree_host.data(), c->tree_host.size(), c->depth, wl.cell_level);
-        c->use_air = al.ok ? 1 : 0;
+        AirLayout al = build_air_layout(c->tree_host.data(), c->tree_host.size(), c->depth);
+        c->use_air = (enable && al.ok) ? 1 : 0;
+        c->air_cell_level = al.cell_level;
+        c->air_top_log2 = al.top_log2;
+        c->air_deep = al.cell_level > 4 ? 1 : 0;
         CU(c->air_top.upload(al.top.data(), al.top.size(), c->stream));
         CU(c->air_wide.upload(al.wide.data(), al.wide.size(), c->stream));
-        CU(c->air_bits.upload(al.bits.data(), al.bits.size(), c->stream));
+        CU(c->air_bricks.upload(al.bricks.data(), al.bricks.size(), c->stream));
     }
-    // BVH stage layout (pair records + aligned triangle blocks); without it kernel 4 falls back to kernel 3 for BVH scenes
+    // BVH stage layout (pair records + aligned triangle blocks); a BVH it cannot hold (malformed, or deeper than the 64 entries
+    // of the reference's traversal stack, bvh.h:38) is rendered by the thread-per-pixel kernel on the reference's own arrays
     {
         BvhLayout wb, ab;
         TriRepack tr;
         std::unordered_map<int, int> leaf_map;
-        const bool we = bvh_is_empty(c->world_head), ae = bvh_is_empty(c->actor_head);
+        const bool we = bvh_is_empty(c->world_host), ae = bvh_is_empty(c->actor_host);
         if (!we) wb.root = bvh_ref(c->world_host, c->trigs_host, 0, 0, wb, tr, leaf_map);
         if (!ae) ab.root = bvh_ref(c->actor_host, c->trigs_host, 0, 0, ab, tr, leaf_map);
         c->use_bvh2 = (wb.ok && ab.ok) ? 1 : 0;
         c->world_root = wb.root;
         c->actor_root = ab.root;
-        if (c->use_bvh2) {
-            CU(c->world_rec.upload(wb.rec.data(), wb.rec.size(), c->stream));
-            CU(c->actor_rec.upload(ab.rec.data(), ab.rec.size(), c->stream));
-            CU(c->tris2.upload(tr.tris.data(), tr.tris.size(), c->stream));
-        }
+        if (!c->use_bvh2) { wb.rec.clear(); ab.rec.clear(); tr.tris.clear(); }
+        CU(c->world_rec.upload(wb.rec.data(), wb.rec.size(), c->stream));
+        CU(c->actor_rec.upload(ab.rec.data(), ab.rec.size(), c->stream));
+        CU(c->tris2.upload(tr.tris.data(), tr.tris.size(), c->stream));
     }
     // sun basis on the device
     if (!c->sun_basis.p) {
@@ -900,57 +756,84 @@ int ccu_scene_commit(ccu_ctx *c) {
     s.sv = make_float3(b[3], b[4], b[5]);
     s.sw = make_float3(b[6], b[7], b[8]);
     s.sun_radius_cos = b[9];
+    c->commit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     c->committed = true;
     return CCU_OK;
 }
 
+// ClCamera.java:33-70 (settings) / :72-105 (pre-generated rays).  Ray uploads go to the buffer no launch is reading, on the
+// copy stream, so that they overlap the passes in flight (the reference's cameraGenTask, OpenClPathTracingRenderer.java:146-148);
+// the next ccu_render_passes uses the new rays.
 int ccu_camera_set(ccu_ctx *c, int32_t projector_type, const float *settings, int64_t n) {
     if (!c || !settings) return fail(CCU_EINVAL, "ccu_camera_set: null argument");
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
-    if (projector_type == -1) {
-        if (n % 6 != 0 || n <= 0) return fail(CCU_EINVAL, "pre-generated rays need 6 floats per pixel (got %lld)", (long long)n);
-        cudaStreamSynchronize(c->stream);    // a render in flight may still read the old rays
-        CU(c->rays.upload(settings, (size_t)n, c->stream));
-    } else {
+    std::lock_guard<std::mutex> cam(c->cam_mu);
+    if (projector_type != -1) {
         if (n < 15) return fail(CCU_EINVAL, "camera settings need 15 floats (got %lld)", (long long)n);
+        std::lock_guard<std::mutex> lk(c->mu);
         memcpy(c->cam, settings, sizeof c->cam);
+        c->projector_type = projector_type;
+        c->have_camera = true;
+        return CCU_OK;
     }
-    c->projector_type = projector_type;
+    if (n % 6 != 0 || n <= 0) return fail(CCU_EINVAL, "pre-generated rays need 6 floats per pixel (got %lld)", (long long)n);
+    int target;
+    cudaEvent_t used;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        target = (c->have_camera && c->projector_type == -1) ? 1 - c->rays_active : c->rays_active;
+        used = c->rays_used[target];
+    }
+    DeviceGuard g(c->device);
+    CU(cudaEventSynchronize(used));              // launches that read this buffer are done (outside the context lock)
+    DevBuf<float> &buf = c->rays[target];        // only camera updates (serialised by cam_mu) touch the inactive buffer
+    if (buf.n != (size_t)n) CU(buf.alloc((size_t)n));
+    CU(cudaMemcpyAsync(buf.p, settings, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaStreamSynchronize(c->copy_stream));   // host memory is not retained past the call
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->rays_active = target;
+    c->projector_type = -1;
     c->have_camera = true;
     return CCU_OK;
 }
 
 int ccu_render_end(ccu_ctx *c) {
     if (!c) return fail(CCU_EINVAL, "ccu_render_end: null context");
-    std::lock_guard<std::mutex> lk(c->mu);
+    int rc = wait_render_stream(c);
+    std::unique_lock<std::mutex> lk(c->mu);
+    const int rc2 = join_merge_locked(c, lk);
     DeviceGuard g(c->device);
-    cudaStreamSynchronize(c->stream);
     stop_timer(c);
     // the buffers stay cached for the next render of the same size (freed by ccu_ctx_destroy / a size change)
     c->target_live = false;
     c->window_spp = 0;
-    return CCU_OK;
+    return rc != CCU_OK ? rc : rc2;
 }
 
 int ccu_render_begin(ccu_ctx *c, int32_t width, int32_t height) {
     if (!c) return fail(CCU_EINVAL, "ccu_render_begin: null context");
     if (width <= 0 || height <= 0 || (int64_t)width * height > (1ll << 30)) return fail(CCU_EINVAL, "bad canvas %dx%d", width, height);
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::unique_lock<std::mutex> lk(c->mu);
+    int rc = join_merge_locked(c, lk);
+    if (rc != CCU_OK) return rc;
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
-    size_t n = (size_t)width * height * 3;
-    if (c->accum && (size_t)c->width * c->height * 3 != n) {
-        cudaFree(c->accum);
-        cudaFreeHost(c->pinned);
-        c->accum = nullptr;
-        c->pinned = nullptr;
+    const size_t align = std::max<size_t>(1, c->accum_align);
+    const size_t n = (((size_t)width * height * 3 + align - 1) / align) * align;
+    if (c->accum[0] && c->accum_floats != n) free_target(c);
+    if (!c->accum[0]) {
+        cudaError_t e = cudaMalloc(&c->accum[0], n * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&c->accum[1], n * sizeof(float));
+        if (e == cudaSuccess) e = cudaMallocHost(&c->pinned, n * sizeof(float));
+        if (e != cudaSuccess) {
+            free_target(c);       // nothing half-allocated survives a failed begin
+            return fail(e == cudaErrorMemoryAllocation ? CCU_ENOMEM : CCU_ECUDA, "ccu_render_begin: %s", cudaGetErrorString(e));
+        }
+        c->accum_floats = n;
+        CU(cudaMemsetAsync(c->accum[1], 0, n * sizeof(float), c->stream));
     }
-    if (!c->accum) {
-        CU(cudaMalloc(&c->accum, n * sizeof(float)));
-        CU(cudaMallocHost(&c->pinned, n * sizeof(float)));
-    }
-    CU(cudaMemsetAsync(c->accum, 0, n * sizeof(float), c->stream));
+    c->accum_active = 0;
+    CU(cudaMemsetAsync(c->accum[0], 0, n * sizeof(float), c->stream));
+    c->window_base = c->accum[0];
     c->width = width;
     c->height = height;
     c->window_spp = 0;
@@ -961,6 +844,8 @@ int ccu_render_begin(ccu_ctx *c, int32_t width, int32_t height) {
 int ccu_render_set_params(ccu_ctx *c, const ccu_render_params *p) {
     if (!c || !p) return fail(CCU_EINVAL, "ccu_render_set_params: null argument");
     if (p->draw_depth < 0 || p->draw_depth >= (1 << 24) || p->max_depth < 1 || p->max_depth > 255) return fail(CCU_EINVAL, "bad render params");
+    if (p->kernel != 0 && p->kernel != 1 && p->kernel != 4) return fail(CCU_EINVAL, "unknown kernel %d (0 auto, 1 thread-per-pixel, 4 wavefront)", p->kernel);
+    if (p->flags & ~(CCU_RENDER_NO_ENTITIES | CCU_RENDER_NO_SUN)) return fail(CCU_EINVAL, "unknown render flags 0x%x", p->flags);
     std::lock_guard<std::mutex> lk(c->mu);
     c->params = *p;
     return CCU_OK;
@@ -969,13 +854,102 @@ int ccu_render_set_params(ccu_ctx *c, const ccu_render_params *p) {
 static int render_ready(ccu_ctx *c, const char *what) {
     if (!c->committed) return fail(CCU_ESTATE, "%s: scene not committed", what);
     if (!c->have_camera) return fail(CCU_ESTATE, "%s: camera not set", what);
-    if (!c->accum || !c->target_live) return fail(CCU_ESTATE, "%s: ccu_render_begin not called", what);
-    if (c->projector_type == -1 && c->rays.n != (size_t)c->width * c->height * 6)
-        return fail(CCU_ESTATE, "%s: ray buffer holds %zu floats, canvas needs %zu", what, c->rays.n, (size_t)c->width * c->height * 6);
+    if (!c->accum[0] || !c->target_live) return fail(CCU_ESTATE, "%s: ccu_render_begin not called", what);
+    if (c->projector_type == -1 && c->rays[c->rays_active].n != (size_t)c->width * c->height * 6)
+        return fail(CCU_ESTATE, "%s: ray buffer holds %zu floats, canvas needs %zu", what, c->rays[c->rays_active].n, (size_t)c->width * c->height * 6);
     return CCU_OK;
 }
 
-static int render_passes_locked(ccu_ctx *c, const int32_t *seeds, int32_t n_passes, bool first_chunk);
+// which implementation closestIntersect runs on: 0 = the reference's own arrays, 1 / 2 = commit-time layouts (2: deep world)
+static int layout_mode(const ccu_ctx *c) { return (c->use_wide && c->use_air) ? (c->air_deep ? 2 : 1) : 0; }
+
+static int render_passes_locked(ccu_ctx *c, const int32_t *seeds, int32_t n_passes, bool first_chunk) {
+    // The seed words are the only per-pass host->device traffic (OpenClPathTracingRenderer.java:106-109).  They are staged in a
+    // small ring of pinned slots so that the call neither retains the caller's array nor waits for the passes in flight.
+    if (!c->seeds_dev) {
+        CU(cudaMalloc(&c->seeds_dev, (size_t)SEED_SLOTS * SEED_SLOT_INTS * sizeof(int)));
+        CU(cudaMallocHost(&c->seeds_pinned, (size_t)SEED_SLOTS * SEED_SLOT_INTS * sizeof(int)));
+        for (int k = 0; k < SEED_SLOTS; k++) CU(cudaEventCreateWithFlags(&c->seeds_ev[k], cudaEventDisableTiming));
+    }
+    const int slot = c->seeds_slot;
+    c->seeds_slot = (slot + 1) % SEED_SLOTS;
+    CU(cudaEventSynchronize(c->seeds_ev[slot]));        // blocks only when SEED_SLOTS batches are already queued
+    int *seeds_host = c->seeds_pinned + (size_t)slot * SEED_SLOT_INTS, *seeds_dev = c->seeds_dev + (size_t)slot * SEED_SLOT_INTS;
+    memcpy(seeds_host, seeds, (size_t)n_passes * sizeof(int));
+    CU(cudaMemcpyAsync(seeds_dev, seeds_host, (size_t)n_passes * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    fill_scene(c);
+    const int n_pixels = c->width * c->height;
+    if (!c->work_counter) CU(cudaMalloc(&c->work_counter, sizeof(unsigned int)));
+    if (first_chunk) CU(cudaEventRecord(c->ev0, c->stream));
+    const bool bvh = !(c->scene.world_bvh_empty && c->scene.actor_bvh_empty);
+    const int mode = layout_mode(c);
+    float *res = c->accum[c->accum_active];
+    const float *res_prev = c->window_spp == 0 ? c->window_base : res;
+    int kernel = c->params.kernel;
+    if (kernel == 0) kernel = (mode != 0 && (!bvh || c->use_bvh2)) ? 4 : 1;   // layouts refused at commit: the reference's own arrays
+    if (kernel == 1) {
+        const int threads = 128, blocks = (n_pixels + threads - 1) / threads;
+        if (mode == 0) k_render_mega<0><<<blocks, threads, 0, c->stream>>>(c->scene, seeds_dev, n_passes, c->window_spp, res, res_prev, n_pixels);
+        else if (mode == 1) k_render_mega<1><<<blocks, threads, 0, c->stream>>>(c->scene, seeds_dev, n_passes, c->window_spp, res, res_prev, n_pixels);
+        else k_render_mega<2><<<blocks, threads, 0, c->stream>>>(c->scene, seeds_dev, n_passes, c->window_spp, res, res_prev, n_pixels);
+    } else {
+        // persistent wavefront kernel (ccu_queue.cuh): one CTA per SM, pixels handed out through a counter
+        if (mode == 0) return fail(CCU_ESTATE, "ccu_render_passes: kernel 4 needs the commit-time octree layouts (malformed octree?)");
+        if (bvh && !c->use_bvh2) return fail(CCU_ESTATE, "ccu_render_passes: kernel 4 cannot hold this BVH (malformed, or deeper than the 64 entries of the reference's traversal stack, bvh.h:38); use kernel 0 or 1");
+        CU(cudaMemsetAsync(c->work_counter, 0, sizeof(unsigned int), c->stream));
+        QueueParams qp;
+        qp.w.seeds = seeds_dev;
+        qp.w.n_passes = n_passes;
+        qp.w.start_spp = c->window_spp;
+        qp.w.res = res;
+        qp.w.res_prev = res_prev;
+        qp.w.n_pixels = n_pixels;
+        qp.w.next_pixel = c->work_counter;
+        qp.yield_below = c->yield_below;
+        qp.refill_min = c->q_refill_min;
+        qp.march_bias = c->q_march_bias;
+        qp.leaf_min = c->q_leaf_min;
+        qp.bvh_warps = c->q_bvh_warps;
+        qp.march_warps = bvh ? 64 : c->q_march_warps;   // with BVHs the service warps are the ones that do not walk
+        const int lay = air_layout_id(c);
+        const int grid = c->sm_count, block = Q_WARPS * 32;
+        const int smem = q_smem_bytes(bvh, lay == 0);
+        if (bvh) {
+            if (lay == 0) k_render_queue<true, 0><<<grid, block, smem, c->stream>>>(c->scene, qp);
+            else if (lay == 1) k_render_queue<true, 1><<<grid, block, smem, c->stream>>>(c->scene, qp);
+            else k_render_queue<true, 2><<<grid, block, smem, c->stream>>>(c->scene, qp);
+        } else {
+            if (lay == 0) k_render_queue<false, 0><<<grid, block, smem, c->stream>>>(c->scene, qp);
+            else if (lay == 1) k_render_queue<false, 1><<<grid, block, smem, c->stream>>>(c->scene, qp);
+            else k_render_queue<false, 2><<<grid, block, smem, c->stream>>>(c->scene, qp);
+        }
+#ifdef CCU_Q_STATS
+        {
+            cudaStreamSynchronize(c->stream);
+            unsigned long long st[32];
+            cudaMemcpyFromSymbol(st, g_qstats, sizeof st);
+            const char *names[4] = {"march", "block", "exit", "end"};
+            fprintf(stderr, "[qstats] ");
+            for (int i = 1; i < 4; i++) fprintf(stderr, "%s: %llu x %.1f lanes  ", names[i], st[2 * i], st[2 * i] ? (double)st[2 * i + 1] / st[2 * i] : 0.0);
+            fprintf(stderr, "\n[qstats] march stages %llu, iterations %llu x %.1f lanes in flight, yields %llu, idle rounds %llu, pops %llu retries %llu\n", st[0], st[10],
+                    st[10] ? (double)st[11] / st[10] : 0.0, st[13], st[12], st[14], st[15]);
+            fprintf(stderr, "[qstats] bvh stages %llu, steps %llu x %.1f walking lanes, leaf turns %llu x %.1f lanes, shade %llu x %.1f lanes\n", st[16], st[18],
+                    st[18] ? (double)st[19] / st[18] : 0.0, st[20], st[20] ? (double)st[21] / st[20] : 0.0, st[22], st[22] ? (double)st[23] / st[22] : 0.0);
+            unsigned long long z[32] = {0};
+            cudaMemcpyToSymbol(g_qstats, z, sizeof z);
+        }
+#endif
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaEventRecord(c->seeds_ev[slot], c->stream));
+    if (c->projector_type == -1) CU(cudaEventRecord(c->rays_used[c->rays_active], c->stream));
+    c->timing_pending = true;
+    c->window_spp += n_passes;
+    c->window_base = res;
+    return CCU_OK;
+}
 
 int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) {
     if (!c) return fail(CCU_EINVAL, "ccu_render_passes: null context");
@@ -985,10 +959,9 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
     if (rc != CCU_OK) return rc;
     if (n_passes == 0) return CCU_OK;
     DeviceGuard g(c->device);
-    stop_timer(c);
-    // one launch covers at most 32768 passes (the default kernel keeps a path's pass index in 16 bits); the reference's
+    // one launch covers at most 32768 passes (the wavefront kernel keeps a path's pass index in 16 bits); the reference's
     // windows are at most 1024 passes (OpenClPathTracingRenderer.java:158)
-    const int32_t kChunk = 32768;
+    const int32_t kChunk = SEED_SLOT_INTS;
     for (int32_t off = 0; off < n_passes; off += kChunk) {
         rc = render_passes_locked(c, seeds + off, std::min(kChunk, n_passes - off), off == 0);
         if (rc != CCU_OK) return rc;
@@ -996,112 +969,12 @@ int ccu_render_passes_async(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) 
     return CCU_OK;
 }
 
-static int render_passes_locked(ccu_ctx *c, const int32_t *seeds, int32_t n_passes, bool first_chunk) {
-    if (c->seeds_cap < n_passes) {
-        cudaStreamSynchronize(c->stream);
-        if (c->seeds_dev) cudaFree(c->seeds_dev);
-        c->seeds_dev = nullptr;
-        c->seeds_cap = 0;
-        CU(cudaMalloc(&c->seeds_dev, (size_t)std::max(n_passes, 1024) * sizeof(int)));
-        c->seeds_cap = std::max(n_passes, 1024);
-    }
-    // the seed words are the only per-pass host->device traffic (OpenClPathTracingRenderer.java:106-109)
-    CU(cudaMemcpyAsync(c->seeds_dev, seeds, (size_t)n_passes * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));   // seeds[] belongs to the caller again
-    fill_scene(c);
-    int n_pixels = c->width * c->height;
-    if (!c->work_counter) CU(cudaMalloc(&c->work_counter, sizeof(unsigned int)));
-    if (first_chunk) CU(cudaEventRecord(c->ev0, c->stream));
-    if (c->params.kernel != 1) CU(cudaMemsetAsync(c->work_counter, 0, sizeof(unsigned int), c->stream));
-    const bool wide = c->scene.use_wide != 0;
-    const bool bvh = !(c->scene.world_bvh_empty && c->scene.actor_bvh_empty);
-#define CCU_DISPATCH(KERNEL, GRID, BLOCK, SMEM, ...)                                                              \
-    do {                                                                                                          \
-        if (bvh && wide) KERNEL<true, true><<<GRID, BLOCK, SMEM, c->stream>>>(__VA_ARGS__);                       \
-        else if (bvh) KERNEL<true, false><<<GRID, BLOCK, SMEM, c->stream>>>(__VA_ARGS__);                        \
-        else if (wide) KERNEL<false, true><<<GRID, BLOCK, SMEM, c->stream>>>(__VA_ARGS__);                       \
-        else KERNEL<false, false><<<GRID, BLOCK, SMEM, c->stream>>>(__VA_ARGS__);                                \
-    } while (0)
-    if (c->params.kernel == 1) {
-        int threads = 128;
-        int blocks = (n_pixels + threads - 1) / threads;
-        if (wide) k_render_mega<true><<<blocks, threads, 0, c->stream>>>(c->scene, c->seeds_dev, n_passes, c->window_spp, c->accum, n_pixels);
-        else k_render_mega<false><<<blocks, threads, 0, c->stream>>>(c->scene, c->seeds_dev, n_passes, c->window_spp, c->accum, n_pixels);
-        c->launches++;
-    } else {
-        // persistent kernels: one resident grid, pixels handed out through a counter
-        WaveParams wp;
-        wp.seeds = c->seeds_dev;
-        wp.n_passes = n_passes;
-        wp.start_spp = c->window_spp;
-        wp.res = c->accum;
-        wp.n_pixels = n_pixels;
-        wp.next_pixel = c->work_counter;
-        wp.wait_lanes = c->wait_lanes;
-        int blocks = c->sm_count * c->blocks_per_sm;
-        if (c->params.kernel == 4 || c->params.kernel == 0) {
-            // CTA-wide path pool with per-stage work masks (ccu_queue.cuh): one CTA per SM - the fastest, hence the default
-            QueueParams qp;
-            qp.w = wp;
-            qp.yield_below = c->yield_below;
-            qp.refill_min = c->q_refill_min;
-            qp.march_bias = c->q_march_bias;
-            qp.leaf_min = c->q_leaf_min;
-            qp.bvh_warps = c->q_bvh_warps;
-            qp.march_warps = bvh ? 64 : c->q_march_warps;   // with BVHs the service warps are the ones that do not walk
-            const bool tops = c->air_top.n <= (size_t)Q_TOP_WORDS && getenv("CCU_NO_TOPS") == nullptr;
-            const int grid = c->sm_count, block = Q_WARPS * 32;
-            if (!c->use_air) return fail(CCU_ESTATE, "ccu_render_passes: kernel 4 needs the air layout (malformed octree?)");
-            if (bvh && !c->use_bvh2) return fail(CCU_ESTATE, "ccu_render_passes: malformed BVH, or deeper than the 64 levels the reference's traversal stack holds (bvh.h:38)");
-            if (tops) {
-                if (bvh) k_render_queue<true, true><<<grid, block, q_smem_bytes(true, true), c->stream>>>(c->scene, qp);
-                else k_render_queue<false, true><<<grid, block, q_smem_bytes(false, true), c->stream>>>(c->scene, qp);
-            } else {
-                if (bvh) k_render_queue<true, false><<<grid, block, q_smem_bytes(true, false), c->stream>>>(c->scene, qp);
-                else k_render_queue<false, false><<<grid, block, q_smem_bytes(false, false), c->stream>>>(c->scene, qp);
-            }
-#ifdef CCU_Q_STATS
-            {
-                cudaStreamSynchronize(c->stream);
-                unsigned long long st[32];
-                cudaMemcpyFromSymbol(st, g_qstats, sizeof st);
-                const char *names[4] = {"march", "block", "exit", "end"};
-                fprintf(stderr, "[qstats] ");
-                for (int i = 1; i < 4; i++) fprintf(stderr, "%s: %llu x %.1f lanes  ", names[i], st[2 * i], st[2 * i] ? (double)st[2 * i + 1] / st[2 * i] : 0.0);
-                fprintf(stderr, "\n[qstats] march stages %llu, iterations %llu x %.1f lanes in flight, yields %llu, idle rounds %llu, pops %llu retries %llu\n", st[0], st[10],
-                        st[10] ? (double)st[11] / st[10] : 0.0, st[13], st[12], st[14], st[15]);
-                fprintf(stderr, "[qstats] bvh stages %llu, steps %llu x %.1f walking lanes, leaf turns %llu x %.1f lanes, shade %llu x %.1f lanes\n", st[16], st[18],
-                        st[18] ? (double)st[19] / st[18] : 0.0, st[20], st[20] ? (double)st[21] / st[20] : 0.0, st[22], st[22] ? (double)st[23] / st[22] : 0.0);
-                unsigned long long z[32] = {0};
-                cudaMemcpyToSymbol(g_qstats, z, sizeof z);
-            }
-#endif
-        } else if (c->params.kernel == 3) {
-            // lane-bound state machine (ccu_wavefront.cuh)
-            CCU_DISPATCH(k_render_wave, blocks, 256, 0, c->scene, wp);
-        } else {
-            // per-warp path pool in shared memory (ccu_pool.cuh)
-            PoolParams pp;
-            pp.w = wp;
-            pp.refill_min = c->refill_min;
-            pp.exit_idle = c->exit_idle;
-            CCU_DISPATCH(k_render_pool, blocks, POOL_WARPS * 32, POOL_SMEM_BYTES, c->scene, pp);
-        }
-        c->launches++;
-    }
-#undef CCU_DISPATCH
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(c->ev1, c->stream));
-    c->timing_pending = true;
-    c->window_spp += n_passes;
-    return CCU_OK;
-}
-
 int ccu_render_sync(ccu_ctx *c) {
     if (!c) return fail(CCU_EINVAL, "ccu_render_sync: null context");
+    int rc = wait_render_stream(c);       // the wait itself runs outside the context lock
+    if (rc != CCU_OK) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    CU(cudaStreamSynchronize(c->stream));
     stop_timer(c);
     return CCU_OK;
 }
@@ -1112,80 +985,72 @@ int ccu_render_passes(ccu_ctx *c, const int32_t *seeds, int32_t n_passes) {
     return ccu_render_sync(c);
 }
 
-static int fetch_mean(ccu_ctx *c) {
-    size_t n = (size_t)c->width * c->height * 3;
-    CU(cudaMemcpyAsync(c->pinned, c->accum, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    stop_timer(c);
-    return CCU_OK;
-}
-
 int ccu_render_read(ccu_ctx *c, float *mean_rgb, int32_t *window_spp) {
     if (!c || !mean_rgb) return fail(CCU_EINVAL, "ccu_render_read: null argument");
-    std::lock_guard<std::mutex> lk(c->mu);
-    if (!c->accum || !c->target_live) return fail(CCU_ESTATE, "ccu_render_read: no render target");
-    DeviceGuard g(c->device);
-    int rc = fetch_mean(c);
+    int rc = wait_render_stream(c);
     if (rc != CCU_OK) return rc;
-    memcpy(mean_rgb, c->pinned, (size_t)c->width * c->height * 3 * sizeof(float));
+    std::unique_lock<std::mutex> lk(c->mu);
+    if (!c->accum[0] || !c->target_live) return fail(CCU_ESTATE, "ccu_render_read: no render target");
+    rc = join_merge_locked(c, lk);
+    if (rc != CCU_OK) return rc;
+    DeviceGuard g(c->device);
+    const size_t n = (size_t)c->width * c->height * 3;
+    CU(cudaMemcpyAsync(c->pinned, c->accum[c->accum_active], n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    stop_timer(c);
+    memcpy(mean_rgb, c->pinned, n * sizeof(float));
     if (window_spp) *window_spp = c->window_spp;
     return CCU_OK;
 }
 
-int ccu_render_merge(ccu_ctx *c, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp) {
+int ccu_render_merge_wait(ccu_ctx *c) {
+    if (!c) return fail(CCU_EINVAL, "ccu_render_merge_wait: null context");
+    std::unique_lock<std::mutex> lk(c->mu);
+    return join_merge_locked(c, lk);
+}
+
+int ccu_render_merge_async(ccu_ctx *c, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp) {
     if (!c || !sample_buffer) return fail(CCU_EINVAL, "ccu_render_merge: null argument");
     if (sample_spp < 0) return fail(CCU_EINVAL, "ccu_render_merge: negative spp");
-    std::lock_guard<std::mutex> lk(c->mu);
-    if (!c->accum || !c->target_live) return fail(CCU_ESTATE, "ccu_render_merge: no render target");
-    DeviceGuard g(c->device);
-    int pass_spp = c->window_spp;
+    std::unique_lock<std::mutex> lk(c->mu);
+    if (!c->accum[0] || !c->target_live) return fail(CCU_ESTATE, "ccu_render_merge: no render target");
+    int rc = join_merge_locked(c, lk);       // one merge at a time: they share the staging buffer and the sample buffer
+    if (rc != CCU_OK) return rc;
+    const int pass_spp = c->window_spp;
     if (merged_spp) *merged_spp = pass_spp;
-    if (pass_spp == 0) {
-        CU(cudaStreamSynchronize(c->stream));
-        stop_timer(c);
-        return CCU_OK;
-    }
-    // OpenClPathTracingRenderer.java:164-173: blocking read of the float buffer, then the spp-weighted merge on the host.
-    // The read-back is cut into chunks so that the merge of chunk k overlaps the copy of chunk k+1.
+    if (pass_spp == 0) return CCU_OK;
+    DeviceGuard g(c->device);
+    // close the window: the passes that follow accumulate in the other buffer (the first of them still reads what this
+    // buffer holds, like the reference's single buffer at bufferSpp = 0, rayTracer.cl:111)
+    CU(cudaEventRecord(c->window_ev, c->stream));
+    const float *src = c->accum[c->accum_active];
+    c->accum_active ^= 1;
+    c->window_base = src;
+    c->window_spp = 0;   // bufferSppReal = 0 (:170)
     const double sinv = 1.0 / (double)(sample_spp + pass_spp);
     const double ds = (double)sample_spp, dp = (double)pass_spp;
     const size_t n = (size_t)c->width * c->height * 3;
-    constexpr int NCH = 8;
-    if (!c->chunk_ev[0]) {
-        for (int k = 0; k < NCH; k++) CU(cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming));
-    }
-    const size_t chunk = ((n + NCH - 1) / NCH + 63) & ~(size_t)63;
-    for (int k = 0; k < NCH; k++) {
-        const size_t lo = std::min(n, k * chunk), hi = std::min(n, (k + 1) * chunk);
-        if (hi > lo) CU(cudaMemcpyAsync(c->pinned + lo, c->accum + lo, (hi - lo) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaEventRecord(c->chunk_ev[k], c->stream));
-    }
-    unsigned hw = std::thread::hardware_concurrency();
-    unsigned nt = std::max(1u, std::min(16u, hw ? hw : 4u));
-    if (n < (1u << 20)) nt = 1;
-    const float *src = c->pinned;
-    cudaEvent_t *evs = c->chunk_ev;
-    const int device = c->device;
-    auto work = [=](unsigned t) {
-        cudaSetDevice(device);
-        for (int k = 0; k < NCH; k++) {
-            const size_t lo = std::min(n, k * chunk), hi = std::min(n, (k + 1) * chunk);
-            cudaEventSynchronize(evs[k]);
-            const size_t len = hi - lo, part = (len + nt - 1) / nt;
-            const size_t a = lo + std::min(len, t * part), b = lo + std::min(len, (t + 1) * part);
-            for (size_t i = a; i < b; i++) sample_buffer[i] = (sample_buffer[i] * ds + (double)src[i] * dp) * sinv;
-        }
-    };
-    if (nt == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
-        for (auto &t : th) t.join();
-    }
-    CU(cudaStreamSynchronize(c->stream));
+    c->merge.active = true;
+    c->merge.status = CCU_OK;
+    c->merge.worker = std::thread([=] {
+        cudaSetDevice(c->device);
+        int st = CCU_OK;
+        cudaError_t e = cudaStreamWaitEvent(c->copy_stream, c->window_ev, 0);
+        if (e != cudaSuccess) st = fail(CCU_ECUDA, "merge: %s", cudaGetErrorString(e));
+        if (st == CCU_OK) st = ccu_host::merge_window_range(c, src, 0, n, sample_buffer, ds, dp, sinv, c->copy_stream, 16);
+        if (st != CCU_OK) { c->merge.status = st; c->merge.error = ccu_host::last_error(); }
+    });
+    return CCU_OK;
+}
+
+int ccu_render_merge(ccu_ctx *c, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp) {
+    int rc = ccu_render_merge_async(c, sample_buffer, sample_spp, merged_spp);
+    if (rc != CCU_OK) return rc;
+    rc = ccu_render_merge_wait(c);
+    if (rc != CCU_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
     stop_timer(c);
-    c->window_spp = 0;   // bufferSppReal = 0 (:170)
     return CCU_OK;
 }
 
@@ -1207,8 +1072,8 @@ int ccu_render_set_window_spp(ccu_ctx *c, int32_t window_spp) {
 int ccu_render_device_buffer(ccu_ctx *c, void **device_ptr, int64_t *n_floats) {
     if (!c || !device_ptr) return fail(CCU_EINVAL, "ccu_render_device_buffer: null argument");
     std::lock_guard<std::mutex> lk(c->mu);
-    if (!c->accum || !c->target_live) return fail(CCU_ESTATE, "ccu_render_device_buffer: no render target");
-    *device_ptr = c->accum;
+    if (!c->accum[0] || !c->target_live) return fail(CCU_ESTATE, "ccu_render_device_buffer: no render target");
+    *device_ptr = c->accum[c->accum_active];
     if (n_floats) *n_floats = (int64_t)c->width * c->height * 3;
     return CCU_OK;
 }
@@ -1216,10 +1081,10 @@ int ccu_render_device_buffer(ccu_ctx *c, void **device_ptr, int64_t *n_floats) {
 int ccu_render_scale(ccu_ctx *c, float factor) {
     if (!c) return fail(CCU_EINVAL, "ccu_render_scale: null context");
     std::lock_guard<std::mutex> lk(c->mu);
-    if (!c->accum || !c->target_live) return fail(CCU_ESTATE, "ccu_render_scale: no render target");
+    if (!c->accum[0] || !c->target_live) return fail(CCU_ESTATE, "ccu_render_scale: no render target");
     DeviceGuard g(c->device);
     size_t n = (size_t)c->width * c->height * 3;
-    k_scale<<<c->sm_count * 4, 256, 0, c->stream>>>(c->accum, factor, n);
+    k_scale<<<c->sm_count * 4, 256, 0, c->stream>>>(c->accum[c->accum_active], factor, n);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -1228,6 +1093,7 @@ int ccu_render_scale(ccu_ctx *c, float factor) {
 
 int ccu_stream_handle(ccu_ctx *c, void **cuda_stream) {
     if (!c || !cuda_stream) return fail(CCU_EINVAL, "ccu_stream_handle: null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
     *cuda_stream = (void *)c->stream;
     return CCU_OK;
 }
@@ -1239,21 +1105,33 @@ int ccu_first_hit(ccu_ctx *c, int32_t seed, int32_t *block, int32_t *face, int32
     int rc = render_ready(c, "ccu_first_hit");
     if (rc != CCU_OK) return rc;
     DeviceGuard g(c->device);
-    stop_timer(c);
     size_t n = (size_t)c->width * c->height;
-    // one scratch allocation: 4 int planes, t, normal(3), color(4) = 12 words per pixel
-    int *scratch = nullptr;
-    CU(cudaMalloc(&scratch, n * 12 * sizeof(int)));
-    int *d_block = scratch, *d_face = scratch + n, *d_node = scratch + 2 * n, *d_kind = scratch + 3 * n;
-    float *d_color = reinterpret_cast<float *>(scratch + 4 * n);          // 16-byte aligned: n*16 bytes offset
-    float *d_t = reinterpret_cast<float *>(scratch + 8 * n);
-    float *d_normal = reinterpret_cast<float *>(scratch + 9 * n);
+    // one scratch allocation (kept for the next call): 4 int planes, colour(4), t, normal(3) = 12 words per pixel
+    if (c->fh_scratch_pixels < n) {
+        cudaStreamSynchronize(c->stream);
+        if (c->fh_scratch) cudaFree(c->fh_scratch);
+        c->fh_scratch = nullptr;
+        c->fh_scratch_pixels = 0;
+        CU(cudaMalloc(&c->fh_scratch, n * 12 * sizeof(int)));
+        c->fh_scratch_pixels = n;
+    }
+    int *scratch = c->fh_scratch;
+    // planes nobody asked for are not written
+    int *d_block = block ? scratch : nullptr, *d_face = face ? scratch + n : nullptr, *d_node = node ? scratch + 2 * n : nullptr,
+        *d_kind = kind ? scratch + 3 * n : nullptr;
+    float *d_color = color ? reinterpret_cast<float *>(scratch + 4 * n) : nullptr;          // 16-byte aligned: n*16 bytes offset
+    float *d_t = t ? reinterpret_cast<float *>(scratch + 8 * n) : nullptr;
+    float *d_normal = normal ? reinterpret_cast<float *>(scratch + 9 * n) : nullptr;
     fill_scene(c);
+    const int mode = layout_mode(c);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
     cudaEventRecord(c->ev0, c->stream);
-    if (c->scene.use_wide) k_first_hit<true><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color);
-    else k_first_hit<false><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color);
+    if (mode == 0) k_first_hit<0><<<blocks, 256, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color);
+    else if (mode == 1) k_first_hit<1><<<blocks, 256, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color);
+    else k_first_hit<2><<<blocks, 256, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color);
     c->launches++;
     cudaEventRecord(c->ev1, c->stream);
+    if (c->projector_type == -1) cudaEventRecord(c->rays_used[c->rays_active], c->stream);
     c->timing_pending = true;
     cudaError_t e = cudaGetLastError();
     auto back = [&](void *dst, const void *src, size_t bytes) {
@@ -1262,7 +1140,6 @@ int ccu_first_hit(ccu_ctx *c, int32_t seed, int32_t *block, int32_t *face, int32
     back(block, d_block, n * 4); back(face, d_face, n * 4); back(node, d_node, n * 4); back(kind, d_kind, n * 4);
     back(t, d_t, n * 4); back(normal, d_normal, n * 12); back(color, d_color, n * 16);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(scratch);
     if (e != cudaSuccess) return fail(CCU_ECUDA, "ccu_first_hit: %s", cudaGetErrorString(e));
     stop_timer(c);
     return CCU_OK;
@@ -1274,16 +1151,19 @@ int ccu_preview(ccu_ctx *c, int32_t *argb) {
     int rc = render_ready(c, "ccu_preview");
     if (rc != CCU_OK) return rc;
     DeviceGuard g(c->device);
-    stop_timer(c);
     size_t n = (size_t)c->width * c->height;
     int *d = nullptr;
     CU(cudaMalloc(&d, n * sizeof(int)));
     fill_scene(c);
+    const int mode = layout_mode(c);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
     cudaEventRecord(c->ev0, c->stream);
-    if (c->scene.use_wide) k_preview<true><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, (int)n, d);
-    else k_preview<false><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, (int)n, d);
+    if (mode == 0) k_preview<0><<<blocks, 256, 0, c->stream>>>(c->scene, (int)n, d);
+    else if (mode == 1) k_preview<1><<<blocks, 256, 0, c->stream>>>(c->scene, (int)n, d);
+    else k_preview<2><<<blocks, 256, 0, c->stream>>>(c->scene, (int)n, d);
     c->launches++;
     cudaEventRecord(c->ev1, c->stream);
+    if (c->projector_type == -1) cudaEventRecord(c->rays_used[c->rays_active], c->stream);
     c->timing_pending = true;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(argb, d, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
@@ -1296,6 +1176,8 @@ int ccu_preview(ccu_ctx *c, int32_t *argb) {
 
 int ccu_last_kernel_ms(ccu_ctx *c, float *ms) {
     if (!c || !ms) return fail(CCU_EINVAL, "ccu_last_kernel_ms: null argument");
+    int rc = wait_render_stream(c);
+    if (rc != CCU_OK) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     stop_timer(c);
@@ -1305,6 +1187,7 @@ int ccu_last_kernel_ms(ccu_ctx *c, float *ms) {
 
 int ccu_launch_count(ccu_ctx *c, int64_t *launches) {
     if (!c || !launches) return fail(CCU_EINVAL, "ccu_launch_count: null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
     *launches = c->launches;
     return CCU_OK;
 }
@@ -1312,8 +1195,17 @@ int ccu_launch_count(ccu_ctx *c, int64_t *launches) {
 int ccu_scene_device_bytes(ccu_ctx *c, int64_t *bytes) {
     if (!c || !bytes) return fail(CCU_EINVAL, "ccu_scene_device_bytes: null argument");
     std::lock_guard<std::mutex> lk(c->mu);
-    *bytes = (int64_t)(c->tree.bytes() + c->top.bytes() + c->wide.bytes() + c->air_top.bytes() + c->air_wide.bytes() + c->air_bits.bytes() + c->world_rec.bytes() + c->actor_rec.bytes() + c->tris2.bytes() + c->block_palette.bytes() + c->quad_models.bytes() + c->aabb_models.bytes() + c->mat_palette.bytes() +
-                       c->trigs.bytes() + c->world_bvh.bytes() + c->actor_bvh.bytes() + c->atlas.bytes() + c->sky.bytes());
+    *bytes = (int64_t)(c->tree.bytes() + c->top.bytes() + c->wide.bytes() + c->air_top.bytes() + c->air_wide.bytes() + c->air_bricks.bytes() +
+                       c->world_rec.bytes() + c->actor_rec.bytes() + c->tris2.bytes() + c->cube_rec.bytes() + c->block_palette.bytes() +
+                       c->quad_models.bytes() + c->aabb_models.bytes() + c->mat_palette.bytes() + c->trigs.bytes() + c->world_bvh.bytes() +
+                       c->actor_bvh.bytes() + c->atlas.bytes() + c->sky.bytes());
+    return CCU_OK;
+}
+
+int ccu_scene_commit_ms(ccu_ctx *c, double *ms) {
+    if (!c || !ms) return fail(CCU_EINVAL, "ccu_scene_commit_ms: null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    *ms = c->commit_ms;
     return CCU_OK;
 }
 
@@ -1383,20 +1275,20 @@ int ccu_bench_gather(ccu_ctx *c, int64_t array_bytes, int32_t dependent, float *
 }
 
 // Host-only check of the commit-time traversal layouts (no CUDA call): for every voxel of `xyz` (count x 3 ints) returns what
-// the value-carrying layout (find_leaf_wide) and the air layout (lean_probe) answer, so that CPU tests can compare both
+// the value-carrying layout (find_leaf_wide) and the march layout (lean_probe) answer, so that CPU tests can compare both
 // with the reference's root descent (octree.h:81-88).
 int ccu_debug_layout_lookup(const int32_t *tree, int64_t n, int32_t depth, const int32_t *xyz, int64_t count, int32_t *wide_value,
                             int32_t *wide_level, int32_t *air_solid, int32_t *air_level) {
     if (!tree || n < 1 || depth < 0 || depth > 30 || (count > 0 && !xyz)) return fail(CCU_EINVAL, "ccu_debug_layout_lookup: bad argument");
     WideLayout wl = build_wide_layout(tree, (size_t)n, depth);
-    AirLayout al = build_air_layout(tree, (size_t)n, depth, wl.cell_level);
+    AirLayout al = build_air_layout(tree, (size_t)n, depth);
     if (!al.ok) return fail(CCU_ESTATE, "air layout could not be built");
     const int cl = wl.cell_level, tl = wl.top_log2;
     for (int64_t i = 0; i < count; i++) {
         const int bx = xyz[3 * i], by = xyz[3 * i + 1], bz = xyz[3 * i + 2];
         if (((bx | by | bz) >> depth) != 0) return fail(CCU_EINVAL, "voxel %lld outside the octree cube", (long long)i);
-        const size_t cell = ((((size_t)(bx >> cl) << tl) + (size_t)(by >> cl)) << tl) + (size_t)(bz >> cl);
         if (wl.ok) {
+            const size_t cell = ((((size_t)(bx >> cl) << tl) + (size_t)(by >> cl)) << tl) + (size_t)(bz >> cl);
             unsigned e = wl.top[cell];
             int lvl = cl;
             while (!(e & CCU_WIDE_LEAF)) {
@@ -1410,20 +1302,25 @@ int ccu_debug_layout_lookup(const int32_t *tree, int64_t n, int32_t depth, const
             if (wide_value) wide_value[i] = -1;
             if (wide_level) wide_level[i] = -1;
         }
-        unsigned e = al.top[cell];
-        int lvl = cl;
-        while (!(e & CCU_WIDE_LEAF)) {
-            if (lvl == 2) {
-                const unsigned v = (unsigned)(((bx & 3) << 4) | ((by & 3) << 2) | (bz & 3));
-                const unsigned code = (al.bits[(size_t)e * 4 + (v >> 4)] >> ((v & 15u) * 2u)) & 3u;
-                e = CCU_WIDE_LEAF | (code == 0 ? 1u : ((code - 1u) << 26));
-                break;
-            }
+        // the lookup of lean_probe (ccu_march.cuh)
+        int lvl = al.cell_level;
+        const int atl = al.top_log2;
+        unsigned e = al.top[((((size_t)(bx >> lvl) << atl) + (size_t)(by >> lvl)) << atl) + (size_t)(bz >> lvl)];
+        while (lvl > 4 && !(e & CCU_WIDE_LEAF)) {
             lvl -= 2;
             e = al.wide[(size_t)e * 64 + ((((bx >> lvl) & 3) << 4) | (((by >> lvl) & 3) << 2) | ((bz >> lvl) & 3))];
         }
-        if (air_solid) air_solid[i] = (int)(e & 1u);
-        if (air_level) air_level[i] = (e & 1u) ? -1 : (int)((e >> 26) & 31);
+        int level;
+        if (e & CCU_WIDE_LEAF) {
+            level = ((int)(e << 1)) >> 27;
+        } else {
+            const unsigned wi = (unsigned)(((bx & 12) << 4) | ((by & 12) << 2) | (bz & 12) | (bx & 3));
+            const unsigned w = al.bricks[(size_t)e * 256 + wi];
+            const int code = (int)((w >> ((((by & 3) << 2) | (bz & 3)) * 2)) & 3u);
+            level = w >= CCU_BRICK_UNIFORM ? (int)(w & 31u) : code - 1;
+        }
+        if (air_solid) air_solid[i] = level < 0 ? 1 : 0;
+        if (air_level) air_level[i] = level;
     }
     return CCU_OK;
 }

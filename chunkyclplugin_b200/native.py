@@ -11,7 +11,11 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchunkycu.so")
+# CHUNKYCU_LIB: load another build of the same library (kernel tuning sweeps build variants next to each other)
+LIB_PATH = os.environ.get("CHUNKYCU_LIB") or os.path.join(_HERE, "libchunkycu.so")
+
+CCU_RENDER_NO_ENTITIES, CCU_RENDER_NO_SUN = 1, 2
+CCU_UNIQUE_ID_BYTES = 128
 
 CCU_OK, CCU_ENODEVICE, CCU_EINVAL, CCU_ECUDA, CCU_ENOMEM, CCU_ESTATE = 0, -1, -2, -3, -4, -5
 
@@ -25,7 +29,7 @@ class ChunkyCuError(RuntimeError):
 
 
 class RenderParams(C.Structure):
-    _fields_ = [("draw_depth", C.c_int32), ("max_depth", C.c_int32), ("emitter_scale", C.c_float), ("kernel", C.c_int32)]
+    _fields_ = [("draw_depth", C.c_int32), ("max_depth", C.c_int32), ("emitter_scale", C.c_float), ("kernel", C.c_int32), ("flags", C.c_int32)]
 
 
 # every symbol include/chunkycu.h declares: name -> (restype, argtypes)
@@ -61,6 +65,8 @@ SYMBOLS = {
     "ccu_render_sync": (C.c_int, [_vp]),
     "ccu_render_read": (C.c_int, [_vp, _vp, _pi32]),
     "ccu_render_merge": (C.c_int, [_vp, _vp, _i32, _pi32]),
+    "ccu_render_merge_async": (C.c_int, [_vp, _vp, _i32, _pi32]),
+    "ccu_render_merge_wait": (C.c_int, [_vp]),
     "ccu_render_reset_window": (C.c_int, [_vp]),
     "ccu_render_set_window_spp": (C.c_int, [_vp, _i32]),
     "ccu_render_end": (C.c_int, [_vp]),
@@ -72,9 +78,27 @@ SYMBOLS = {
     "ccu_last_kernel_ms": (C.c_int, [_vp, C.POINTER(_f)]),
     "ccu_launch_count": (C.c_int, [_vp, C.POINTER(_i64)]),
     "ccu_scene_device_bytes": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "ccu_scene_commit_ms": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "ccu_tonemap": (C.c_int, [_vp, _i32, _i32, _f, _vp, _i32, _vp]),
     "ccu_bench_gather": (C.c_int, [_vp, _i64, _i32, C.POINTER(_f), C.POINTER(_f)]),
     "ccu_debug_layout_lookup": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    # multi-GPU
+    "ccu_group_create": (C.c_int, [_vp, _i32, C.POINTER(_vp)]),
+    "ccu_group_unique_id": (C.c_int, [_vp]),
+    "ccu_group_join": (C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(_vp)]),
+    "ccu_group_destroy": (C.c_int, [_vp]),
+    "ccu_group_size": (C.c_int, [_vp, _pi32, _pi32]),
+    "ccu_group_member": (C.c_int, [_vp, _i32, C.POINTER(_vp)]),
+    "ccu_group_replicate_scene": (C.c_int, [_vp]),
+    "ccu_group_camera_set": (C.c_int, [_vp, _i32, _vp, _i64]),
+    "ccu_group_render_begin": (C.c_int, [_vp, _i32, _i32]),
+    "ccu_group_render_set_params": (C.c_int, [_vp, C.POINTER(RenderParams)]),
+    "ccu_group_render_passes": (C.c_int, [_vp, _vp, _i32]),
+    "ccu_group_render_sync": (C.c_int, [_vp]),
+    "ccu_group_render_merge": (C.c_int, [_vp, _vp, _i32, _pi32]),
+    "ccu_group_render_reduce": (C.c_int, [_vp, _pi32]),
+    "ccu_group_render_end": (C.c_int, [_vp]),
+    "ccu_group_last_ms": (C.c_int, [_vp, C.POINTER(_f), C.POINTER(_f)]),
 }
 
 _lib = None
@@ -132,16 +156,21 @@ def device_info(index: int) -> dict:
 class Context:
     """Owns one ccu_ctx (one CUDA device)."""
 
-    def __init__(self, device_index: int = 0):
+    def __init__(self, device_index: int = 0, _borrowed=None):
         self._lib = load()
-        h = C.c_void_p()
-        check(self._lib.ccu_ctx_create(device_index, C.byref(h)))
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            h = C.c_void_p()
+            check(self._lib.ccu_ctx_create(device_index, C.byref(h)))
+        else:
+            h = _borrowed          # a member context owned by a Group
         self._h = h
         self.device_index = device_index
 
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.ccu_ctx_destroy(self._h)
+            if self._owned:
+                self._lib.ccu_ctx_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -210,8 +239,8 @@ class Context:
         check(self._lib.ccu_render_begin(self._h, width, height))
         self._wh = (width, height)
 
-    def render_set_params(self, draw_depth=256, max_depth=5, emitter_scale=13.0, kernel=0):
-        p = RenderParams(draw_depth, max_depth, emitter_scale, kernel)
+    def render_set_params(self, draw_depth=256, max_depth=5, emitter_scale=13.0, kernel=0, flags=0):
+        p = RenderParams(draw_depth, max_depth, emitter_scale, kernel, flags)
         check(self._lib.ccu_render_set_params(self._h, C.byref(p)))
 
     def render_passes(self, seeds, block: bool = True):
@@ -235,6 +264,18 @@ class Context:
         m = C.c_int32()
         check(self._lib.ccu_render_merge(self._h, _ptr(sample_buffer), sample_spp, C.byref(m)))
         return m.value
+
+    def render_merge_async(self, sample_buffer: np.ndarray, sample_spp: int) -> int:
+        """Closes the window and merges it in the background; ``sample_buffer`` must stay alive until render_merge_wait()."""
+        assert sample_buffer.dtype == np.float64 and sample_buffer.flags.c_contiguous
+        m = C.c_int32()
+        check(self._lib.ccu_render_merge_async(self._h, _ptr(sample_buffer), sample_spp, C.byref(m)))
+        self._merge_keepalive = sample_buffer
+        return m.value
+
+    def render_merge_wait(self):
+        check(self._lib.ccu_render_merge_wait(self._h))
+        self._merge_keepalive = None
 
     def render_reset_window(self):
         check(self._lib.ccu_render_reset_window(self._h))
@@ -303,3 +344,102 @@ class Context:
         n = C.c_int64()
         check(self._lib.ccu_scene_device_bytes(self._h, C.byref(n)))
         return n.value
+
+    def scene_commit_ms(self) -> float:
+        ms = C.c_double()
+        check(self._lib.ccu_scene_commit_ms(self._h, C.byref(ms)))
+        return ms.value
+
+
+def group_unique_id() -> bytes:
+    """NCCL unique id for a one-process-per-GPU group: rank 0 calls this and the host distributes the 128 bytes."""
+    buf = C.create_string_buffer(CCU_UNIQUE_ID_BYTES)
+    check(load().ccu_group_unique_id(buf))
+    return buf.raw
+
+
+class Group:
+    """N GPUs of one box rendering one image: ccu_group_* (include/chunkycu.h, "multi-GPU").
+
+    ``Group(devices=[0, 1, ...])`` drives all GPUs from this process (what a JVM plugin does);
+    ``Group(ctx=ctx, unique_id=..., rank=r, world=N)`` wraps this process's context in a one-process-per-GPU job."""
+
+    def __init__(self, devices=None, ctx: Optional[Context] = None, unique_id: Optional[bytes] = None, rank: int = 0, world: int = 1):
+        self._lib = load()
+        h = C.c_void_p()
+        if devices is not None:
+            d = np.ascontiguousarray(devices, dtype=np.int32)
+            check(self._lib.ccu_group_create(_ptr(d), d.size, C.byref(h)))
+            self._ctx_keep = None
+        else:
+            assert ctx is not None
+            uid = C.create_string_buffer(unique_id, CCU_UNIQUE_ID_BYTES) if unique_id is not None else None
+            check(self._lib.ccu_group_join(ctx._h, uid, rank, world, C.byref(h)))
+            self._ctx_keep = ctx
+        self._h = h
+        w, l = C.c_int32(), C.c_int32()
+        check(self._lib.ccu_group_size(self._h, C.byref(w), C.byref(l)))
+        self.world, self.local_members = w.value, l.value
+        self.rank = rank if devices is None else 0
+        self._wh = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ccu_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def member(self, i: int) -> Context:
+        h = C.c_void_p()
+        check(self._lib.ccu_group_member(self._h, i, C.byref(h)))
+        if self._ctx_keep is not None:
+            return self._ctx_keep
+        c = Context(_borrowed=h)
+        return c
+
+    def replicate_scene(self):
+        check(self._lib.ccu_group_replicate_scene(self._h))
+
+    def camera_set(self, projector_type: int, settings):
+        a = np.ascontiguousarray(settings, dtype=np.float32)
+        check(self._lib.ccu_group_camera_set(self._h, projector_type, _ptr(a), a.size))
+
+    def render_begin(self, width: int, height: int):
+        check(self._lib.ccu_group_render_begin(self._h, width, height))
+        self._wh = (width, height)
+
+    def render_set_params(self, draw_depth=256, max_depth=5, emitter_scale=13.0, kernel=0, flags=0):
+        p = RenderParams(draw_depth, max_depth, emitter_scale, kernel, flags)
+        check(self._lib.ccu_group_render_set_params(self._h, C.byref(p)))
+
+    def render_passes(self, seeds):
+        a = np.ascontiguousarray(seeds, dtype=np.int32)
+        check(self._lib.ccu_group_render_passes(self._h, _ptr(a), a.size))
+
+    def render_sync(self):
+        check(self._lib.ccu_group_render_sync(self._h))
+
+    def render_merge(self, sample_buffer: np.ndarray, sample_spp: int) -> int:
+        assert sample_buffer.dtype == np.float64 and sample_buffer.flags.c_contiguous
+        m = C.c_int32()
+        check(self._lib.ccu_group_render_merge(self._h, _ptr(sample_buffer), sample_spp, C.byref(m)))
+        return m.value
+
+    def reduce_only(self) -> int:
+        """Reduce-scatter of the open window without the read-back (the sums stay on the GPUs); returns the window's passes."""
+        m = C.c_int32()
+        check(self._lib.ccu_group_render_reduce(self._h, C.byref(m)))
+        return m.value
+
+    def render_end(self):
+        check(self._lib.ccu_group_render_end(self._h))
+
+    def last_ms(self):
+        a, b = C.c_float(), C.c_float()
+        check(self._lib.ccu_group_last_ms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value

@@ -17,6 +17,7 @@ host that stands in for it: same class roles, method names, call order and error
 from __future__ import annotations
 
 import threading
+import time
 from typing import Callable, Optional
 
 import numpy as np
@@ -32,8 +33,11 @@ from .scenes import PackedScene
 class Scene:
     """What the renderers use of se.llbit.chunky.renderer.scene.Scene."""
 
-    def __init__(self, packed: PackedScene, target_spp: int = 16):
+    def __init__(self, packed: PackedScene, target_spp: int = 16, ray_generator: Optional[Callable[[bool], np.ndarray]] = None):
         self.packed = packed
+        # projectorType -1 only: stands in for Camera.calcViewRay over all pixels (ClCamera.java:75-97); called with
+        # jitter on/off, returns float32[6*W*H].  Without it the rays stored in the packed scene are used as they are.
+        self.ray_generator = ray_generator
         self.width, self.height = packed.width, packed.height
         self.sample_buffer = np.zeros(self.width * self.height * 3, dtype=np.float64)   # getSampleBuffer()
         self.back_buffer = np.zeros(self.width * self.height, dtype=np.int32)           # getBackBuffer().data
@@ -158,17 +162,17 @@ class CudaCamera:
         if not self.needGenerate:
             self.instance.context.camera_set(self.projectorType, scene.packed.camera[:15])
 
-    def generate(self, renderLock=None, jitter: bool = True):
+    def generate(self, renderLock=None, jitter: bool = True):          # :72-105
         if not self.needGenerate:
             return
-        rays = self.scene.packed.camera        # pre-generated by the host (Chunky's Camera.calcViewRay in the reference)
-        if renderLock is not None:
-            renderLock.acquire()
-        try:
-            self.instance.context.camera_set(-1, rays)
-        finally:
-            if renderLock is not None:
-                renderLock.release()
+        gen = getattr(self.scene, "ray_generator", None)
+        # fresh sub-pixel jitter per call (ThreadLocalRandom in the reference, :83-87); the packed rays are the jitter-free set
+        rays = gen(jitter) if gen is not None else self.scene.packed.camera
+        # The reference takes renderLock around the upload because its queue is shared with the pass loop (:99-104).  Here the
+        # library uploads into the ray buffer no launch is reading, on its copy stream, so the upload overlaps the passes in
+        # flight and the next ccu_render_passes picks the new rays up; the lock is not needed.
+        self.instance.context.camera_set(-1, rays)
+        self.generations = getattr(self, "generations", 0) + 1
 
     def close(self): pass
 
@@ -178,13 +182,21 @@ class CudaCamera:
 # ----------------------------------------------------------------------------------------------------
 class CudaPathTracingRenderer:
     MERGE_WINDOW = 1024                                       # :158
+    CALLBACK_MS = 100.0                                       # :153-157 postRender is polled at most every 100 ms
 
-    def __init__(self, sceneLoader: Optional[CudaSceneLoader] = None, passes_per_call: int = 0):
+    def __init__(self, sceneLoader: Optional[CudaSceneLoader] = None, passes_per_call: int = 0, merge_window: Optional[int] = None,
+                 camera_regen_passes: int = 8):
         self.sceneLoader = sceneLoader or CudaSceneLoader()
         self.postRender: Callable[[], bool] = lambda: False   # Chunky passes a callback that returns true to stop
-        # how many passes one C-ABI call may cover (0 = up to the next merge point); the reference issues 1 per launch
+        # How many passes one C-ABI call may cover.  The reference issues 1 per launch and polls postRender at most every
+        # 100 ms; here a call covers as many passes as fit in about CALLBACK_MS of device time (measured, so heavy scenes get
+        # short batches and the UI stays responsive), never more than up to the next merge point.  > 0 pins the batch size.
         self.passes_per_call = passes_per_call
+        self.merge_window = merge_window or self.MERGE_WINDOW
+        # projectorType -1: passes rendered with one set of camera rays before a freshly jittered set may replace it
+        self.camera_regen_passes = max(1, camera_regen_passes)
         self.kernel_ms = 0.0
+        self._ms_per_pass: Optional[float] = None             # device time per pass of the last batch (kept across renders)
 
     def getId(self): return "ChunkyClRenderer"               # :33-36 - the renderer selector id is unchanged
     def getName(self): return "ChunkyClRenderer"
@@ -194,6 +206,13 @@ class CudaPathTracingRenderer:
 
     def sceneReset(self, manager: DefaultRenderManager, reason: str, resetCount: int):     # :203-205
         self.sceneLoader.load(resetCount, reason, manager.bufferedScene)
+
+    def _batch_limit(self) -> int:
+        if self.passes_per_call > 0:
+            return self.passes_per_call
+        if self._ms_per_pass is None:
+            return 1                                         # first call: one pass, to learn what a pass costs
+        return max(1, int(self.CALLBACK_MS / max(self._ms_per_pass, 1e-3)))
 
     def render(self, manager: DefaultRenderManager):         # :54-191
         instance = self.sceneLoader.instance
@@ -205,6 +224,23 @@ class CudaPathTracingRenderer:
         self.sceneLoader.ensureLoad(scene)                   # :64
         camera = CudaCamera(scene, instance)                 # :70
         ctx.render_begin(scene.width, scene.height)          # :71-78
+        cameraGenTask: Optional[threading.Thread] = None
+        cameraErrors = []
+        mergePending = [False]
+
+        def finishMerge():                                   # bufferMergeTask.join() + the tail of the merge task (:174-176)
+            if mergePending[0]:
+                ctx.render_merge_wait()
+                mergePending[0] = False
+                scene.postProcessFrame()
+                manager.redrawScreen()
+
+        def cameraGen():
+            try:
+                camera.generate(renderLock, True)
+            except Exception as e:                           # surfaced on the render thread
+                cameraErrors.append(e)
+
         try:
             camera.generate(renderLock, True)                # :88
             bufferSppReal = 0
@@ -212,13 +248,15 @@ class CudaPathTracingRenderer:
             sceneSpp = scene.spp
             rand = JavaRandom(0)                             # :95
             self.kernel_ms = 0.0
+            lastCallback = 0.0
             while logicalSpp < scene.getTargetSpp():         # :102
                 # The reference issues one pass per launch and tests for a save event after each (:150).  Here one
-                # C-ABI call covers all passes up to the next point where the reference would merge: the next save
-                # event (snapshot / dump / target spp) or a full window - found by probing the same predicate.
-                n = self.MERGE_WINDOW - bufferSppReal
-                if self.passes_per_call > 0:
-                    n = min(n, self.passes_per_call)
+                # C-ABI call covers all passes up to the next point where the reference would merge - the next save
+                # event (snapshot / dump / target spp) or a full window, found by probing the same predicate - but no
+                # more than the batch limit (about 100 ms of device time, or camera_regen_passes with generated rays).
+                n = max(1, min(self.merge_window - bufferSppReal, self._batch_limit()))
+                if camera.needGenerate:
+                    n = min(n, self.camera_regen_passes)
                 control = manager.getSnapshotControl()
                 for k in range(1, n + 1):
                     if self._isSaveEvent(control, scene, logicalSpp + bufferSppReal + k):
@@ -227,27 +265,50 @@ class CudaPathTracingRenderer:
                 seeds = np.array([rand.next_int() for _ in range(n)], dtype=np.int32)      # :106-107
                 with renderLock:
                     ctx.render_passes(seeds)                 # :108-141 (bufferSpp tracked by the library)
-                self.kernel_ms += ctx.last_kernel_ms()
+                ms = ctx.last_kernel_ms()
+                self.kernel_ms += ms
+                self._ms_per_pass = ms / n
                 bufferSppReal += n                           # :143-144
                 scene.spp += n
+                if cameraErrors:
+                    raise cameraErrors[0]
+                if camera.needGenerate and (cameraGenTask is None or not cameraGenTask.is_alive()):    # :146-148
+                    cameraGenTask = threading.Thread(target=cameraGen, daemon=True)
+                    cameraGenTask.start()
                 saveEvent = self._isSaveEvent(manager.getSnapshotControl(), scene, logicalSpp + bufferSppReal)
                 if not scene.shouldFinalizeBuffer() and not saveEvent:
-                    if self.postRender():                    # :153-157
-                        break
-                    if bufferSppReal < self.MERGE_WINDOW:    # :158-159
+                    now = time.monotonic() * 1e3
+                    if now - lastCallback > self.CALLBACK_MS and not manager.shouldFinalize():    # :153-157
+                        lastCallback = now
+                        if self.postRender():
+                            break
+                    if bufferSppReal < self.merge_window:    # :158-159
                         continue
+                finishMerge()                                # :162 bufferMergeTask.join()
                 if self.postRender():                        # :163
                     break
-                passSpp = ctx.render_merge(sampleBuffer, sceneSpp)     # :164-173 (read + weighted merge, window reset)
+                # :164-173 read + weighted merge + window reset; like the reference's ForkJoin task the merge runs in the
+                # background (copy stream + worker threads of the library) while the next passes render
+                passSpp = ctx.render_merge_async(sampleBuffer, sceneSpp)
+                mergePending[0] = True
                 assert passSpp == bufferSppReal
                 sceneSpp += passSpp
                 bufferSppReal = 0
-                scene.postProcessFrame()                     # :175-176
-                manager.redrawScreen()
                 logicalSpp += passSpp                        # :178
+                if saveEvent:                                # :179-182
+                    finishMerge()
+                    if self.postRender():
+                        break
         finally:
-            camera.close()
-            ctx.render_end()
+            if cameraGenTask is not None:
+                cameraGenTask.join()                         # :186
+            try:
+                finishMerge()                                # :187
+            finally:
+                camera.close()
+                ctx.render_end()
+        if cameraErrors:
+            raise cameraErrors[0]
 
     @staticmethod
     def _isSaveEvent(control: SnapshotControl, scene: Scene, spp: int) -> bool:           # :193-195

@@ -400,16 +400,19 @@ def pinhole_camera(pos, yaw_deg: float, pitch_deg: float, fov_deg: float = 70.0,
     return out.astype(np.float32)
 
 
-def pregenerated_rays(cam15: np.ndarray, width: int, height: int) -> np.ndarray:
-    """float[6*W*H] (o,d) per pixel at pixel centres - the projectorType -1 path (ClCamera.java:72-105)."""
+def pregenerated_rays(cam15: np.ndarray, width: int, height: int, jitter: Optional[np.random.Generator] = None) -> np.ndarray:
+    """float[6*W*H] (o,d) per pixel - the projectorType -1 path (ClCamera.java:72-105): pixel centres, or a fresh
+    sub-pixel offset per pixel when a generator is given (the reference's jitter, ClCamera.java:83-87)."""
     pos = cam15[0:3].astype(np.float64)
     m = cam15[3:12].astype(np.float64).reshape(3, 3)
     fov_tan = float(cam15[14])
     half_w = width / (2.0 * height)
     inv_h = 1.0 / height
     px, py = np.meshgrid(np.arange(width), np.arange(height))
-    x = -half_w + (px + 0.5) * inv_h
-    y = -0.5 + (py + 0.5) * inv_h
+    ox = jitter.random((height, width), dtype=np.float32) if jitter is not None else 0.5
+    oy = jitter.random((height, width), dtype=np.float32) if jitter is not None else 0.5
+    x = -half_w + (px + ox) * inv_h
+    y = -0.5 + (py + oy) * inv_h
     d = np.stack([fov_tan * x, fov_tan * y, np.ones_like(x)], axis=-1)
     d = d / np.linalg.norm(d, axis=-1, keepdims=True)
     d = d @ m.T

@@ -42,8 +42,15 @@ typedef struct ccu_render_params {
     int32_t draw_depth;    /* octree march step limit */
     int32_t max_depth;     /* ray depth limit (5 = 4 bounces) */
     float emitter_scale;   /* emitter intensity factor */
-    int32_t kernel;        /* 0 = auto (currently 4), 1 = thread-per-pixel megakernel, 2 = persistent wavefront with per-warp path pool in shared memory, 3 = persistent wavefront with lane-bound paths, 4 = persistent wavefront with a CTA-wide path pool and per-stage work masks */
+    int32_t kernel;        /* 0 = auto (4 when the commit-time layouts could be built, else 1), 1 = thread-per-pixel kernel (one launch per batch; cross-check and fallback), 4 = persistent wavefront kernel with a CTA-wide path pool and per-stage work masks */
+    int32_t flags;         /* CCU_RENDER_* bits: Chunky's scene toggles as launch parameters (reference README.md:31-35) */
 } ccu_render_params;
+/* "Draw entities" unchecked: both entity BVHs are treated as empty (the reference gets EMPTY_NODE uploads from Chunky,
+ * AbstractSceneLoader.java:118-127) without touching the uploaded scene. */
+#define CCU_RENDER_NO_ENTITIES 1
+/* Sunlight disabled (indoor scenes): bit 0 of the sun flags (PackedSun.java:16, tested at sky.h:45,69) reads as 0 - no sun
+ * sampling, no sun disc - without re-uploading sunData. */
+#define CCU_RENDER_NO_SUN 2
 
 /* ---- device enumeration: RendererInstance.java:39-75,123-157 (clGetPlatformIDs/clGetDeviceIDs/clGetDeviceInfo),
  *      used by the GPU selector UI (ui/GpuSelector.java:24-87) -------------------------------------------------- */
@@ -95,6 +102,12 @@ int ccu_render_read(ccu_ctx *ctx, float *mean_rgb, int32_t *window_spp);
 /* :167-173 fused read + merge into Chunky's double sample buffer:
  *   sample[i] = (sample[i]*sample_spp + mean[i]*window_spp) / (sample_spp + window_spp); then the window restarts (:170) */
 int ccu_render_merge(ccu_ctx *ctx, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp);
+/* :150-151,172-177 the reference merges in a ForkJoin task while the next passes render.  ccu_render_merge_async does the same:
+ * it closes the window (the next passes go to a second accumulation buffer), starts the read-back on a copy stream and the
+ * spp-weighted merge on worker threads, and returns.  `sample_buffer` must stay valid until ccu_render_merge_wait (or the next
+ * merge / ccu_render_end, which wait implicitly).  *merged_spp = passes of the closed window. */
+int ccu_render_merge_async(ccu_ctx *ctx, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp);
+int ccu_render_merge_wait(ccu_ctx *ctx);   /* bufferMergeTask.join() */
 int ccu_render_reset_window(ccu_ctx *ctx); /* bufferSppReal = 0 (:170); the buffer itself is not cleared, as in the reference */
 /* multi-GPU: after the window buffers of all ranks have been reduced into this context's buffer (mean over all passes), tell it how
  * many passes the buffer now stands for, so that ccu_render_merge / ccu_render_read weight it correctly (bufferSppReal of :167-173) */
@@ -128,6 +141,7 @@ int ccu_tonemap(ccu_ctx *ctx, int32_t width, int32_t height, float exposure, con
 int ccu_last_kernel_ms(ccu_ctx *ctx, float *ms);          /* CUDA-event time of the last render_passes / first_hit launch(es) */
 int ccu_launch_count(ccu_ctx *ctx, int64_t *launches);    /* kernels launched by this context so far */
 int ccu_scene_device_bytes(ccu_ctx *ctx, int64_t *bytes); /* HBM held by the committed scene */
+int ccu_scene_commit_ms(ccu_ctx *ctx, double *ms);        /* host time the last ccu_scene_commit spent building + uploading the layouts */
 /* Memory-system denominators for this path's roofline (dependent 32-byte-sector gathers): random 16-byte
  * L2 loads over an array of `array_bytes` (4 MB = L2 resident, 1 GB = HBM resident); dependent = 1 walks a pointer chain
  * (ns_per_load = latency of one dependent gather), 0 issues independent loads (gbytes_per_s = sector bandwidth). */
@@ -138,6 +152,43 @@ int ccu_bench_gather(ccu_ctx *ctx, int64_t array_bytes, int32_t dependent, float
  * root descent (octree.h:81-88, ClSceneLoader.java:56-59 numbering); used by the CPU test-suite. */
 int ccu_debug_layout_lookup(const int32_t *tree, int64_t n, int32_t depth, const int32_t *xyz, int64_t count, int32_t *wide_value,
                             int32_t *wide_level, int32_t *air_solid, int32_t *air_level);
+
+/* ---- multi-GPU: samples-per-pixel split over the GPUs of one box -------------------------------------------
+ * The reference is one JVM and one device (RendererInstance.java:81-101).  A group is N contexts, each holding a full scene
+ * replica; pass p of a window goes to member p mod N with the seed it would have had on one GPU (state = seed_p + gid,
+ * rayTracer.cl:55), so the union of samples equals the 1-GPU run.  The only exchange is the sum of the per-GPU window buffers:
+ * an NCCL reduce-scatter over NVLink, after which EVERY GPU copies its 1/N share to the host over its own PCIe link and the
+ * shares are merged into the sample buffer in parallel (OpenClPathTracingRenderer.java:164-173 with passSpp = all passes).
+ *
+ * Two ways to form a group:
+ *   ccu_group_create      one process drives all GPUs (the JVM plugin): ncclCommInitAll + one worker thread per device;
+ *   ccu_group_join        one process per GPU (torchrun): every rank wraps its own context; rank 0 obtains an id with
+ *                         ccu_group_unique_id and the host distributes it (any channel) before the collective join.
+ * Scene: upload + commit on member 0 as usual, then ccu_group_replicate_scene copies the committed scene (layouts included)
+ * to the other members device-to-device; with ccu_group_join every rank uploads its own replica. */
+typedef struct ccu_group ccu_group;
+#define CCU_UNIQUE_ID_BYTES 128
+int ccu_group_create(const int32_t *devices, int32_t n, ccu_group **out);
+int ccu_group_unique_id(uint8_t id[CCU_UNIQUE_ID_BYTES]);
+int ccu_group_join(ccu_ctx *ctx, const uint8_t id[CCU_UNIQUE_ID_BYTES], int32_t rank, int32_t world, ccu_group **out);
+int ccu_group_destroy(ccu_group *g);
+int ccu_group_size(ccu_group *g, int32_t *world, int32_t *local_members);
+int ccu_group_member(ccu_group *g, int32_t local_index, ccu_ctx **ctx);   /* borrowed; owned by the group for ccu_group_create */
+int ccu_group_replicate_scene(ccu_group *g);                              /* member 0 -> all local members, over NVLink */
+int ccu_group_camera_set(ccu_group *g, int32_t projector_type, const float *settings, int64_t n_floats);
+int ccu_group_render_begin(ccu_group *g, int32_t width, int32_t height);
+int ccu_group_render_set_params(ccu_group *g, const ccu_render_params *p);
+/* seeds of ALL passes of the batch in 1-GPU order; member of global rank r renders passes r, r+N, ... (asynchronously) */
+int ccu_group_render_passes(ccu_group *g, const int32_t *seeds, int32_t n_passes);
+int ccu_group_render_sync(ccu_group *g);
+/* reduce-scatter of the window sums, per-GPU read-back of its share, merge into sample_buffer (all shares with ccu_group_create;
+ * only this rank's share - sample_buffer must then be memory shared by all ranks - with ccu_group_join).  Collective. */
+int ccu_group_render_merge(ccu_group *g, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp);
+/* only the device part of the merge: reduce-scatter of the open window (closes it; the sums stay on the GPUs until the next
+ * ccu_group_render_merge reads them back).  *window_spp = passes of the window.  Collective. */
+int ccu_group_render_reduce(ccu_group *g, int32_t *window_spp);
+int ccu_group_render_end(ccu_group *g);
+int ccu_group_last_ms(ccu_group *g, float *render_ms, float *reduce_ms);   /* device time of the last batch (max over local members) / last reduce-scatter */
 
 #ifdef __cplusplus
 }

@@ -38,11 +38,12 @@ def test_reference_arm_other_ranks_stay_silent():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    d = _run(["--steps", "2", "--warmup", "3"])
+    d = _run(["--steps", "2", "--warmup", "3", "--no-other-workloads"])
     assert BASE_KEYS | {"roofline", "clocks", "gpu_launches", "primary_rays", "memory_system"} <= set(d)
     assert d["gpu_launches"] >= 2 and d["n_gpus"] == 1 and d["dtype"] == "f32" and d["data"] == "synthetic"
     rf = d["roofline"]
-    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["traffic"]
+    assert rf["bound"] == "l2_random_sector" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert 0 < rf["frac_hbm_nominal"] < rf["frac"] * 2 and d["scene_commit_ms"] > 0
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 4 * 3 * 1920 * 1080 and 0 < e["value"] <= d["value"] * 1.05
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0

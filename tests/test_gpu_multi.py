@@ -1,9 +1,13 @@
-"""Sample-parallel rendering across 2 GPUs (NCCL): N-GPU image == 1-GPU image up to fp32 summation order."""
+"""Sample-parallel rendering through the library's group API (ccu_group_*): N-GPU image == 1-GPU image up to fp32
+summation order.  The 1-member group runs on any GPU box; the 2-GPU cases skip (loudly) below 2 devices."""
 import os
 import socket
 
 import numpy as np
 import pytest
+
+from chunkyclplugin_b200.javarandom import pass_seeds
+from conftest import load_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -16,91 +20,118 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_passes, out_path):
-    import torch
-    import torch.distributed as dist
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    try:
-        from chunkyclplugin_b200 import native, scenes as S
-        from chunkyclplugin_b200.javarandom import pass_seeds
-        from chunkyclplugin_b200.multigpu import SampleParallelRenderer
-        from conftest import load_scene
-        p = S.terrain_scene(64, 160, 90, seed=7)
-        ctx = native.Context(rank)
-        load_scene(ctx, p)
-        spr = SampleParallelRenderer(ctx, rank, world)
-        n_local = spr.render_window(pass_seeds(n_passes))
-        out, n = spr.reduce_window(n_local)
-        if rank == 0:
-            assert n == n_passes
-            np.save(out_path, out.cpu().numpy())
-        ctx.close()
-    finally:
-        dist.destroy_process_group()
+def _n_gpus():
+    from chunkyclplugin_b200 import native
+    return native.device_count()
 
 
-def test_two_gpu_reduce_matches_one_gpu(tmp_path, scenes, cuda_ctx):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    import torch.multiprocessing as mp
-    from chunkyclplugin_b200.javarandom import pass_seeds
-    from conftest import load_scene
-    n_passes = 7
-    out_path = str(tmp_path / "combined.npy")
-    mp.spawn(_worker, args=(2, _free_port(), n_passes, out_path), nprocs=2, join=True)
-    combined = np.load(out_path)
-    p = scenes("terrain64")
+def _one_gpu_merge(cuda_ctx, p, n_passes, sample_spp, base):
     load_scene(cuda_ctx, p)
     cuda_ctx.render_passes(pass_seeds(n_passes))
     one, _ = cuda_ctx.render_read()
-    assert np.allclose(combined, one, rtol=2e-6, atol=1e-7)
+    return (base * sample_spp + one.astype(np.float64) * n_passes) / (sample_spp + n_passes)
 
 
-def _worker_merge(rank, world, port, n_passes, out_path):
-    import torch
+def _load_group_scene(group, p):
+    m0 = group.member(0)
+    load_scene(m0, p)                       # upload + commit on member 0 only ...
+    m0.render_end()
+    group.replicate_scene()                 # ... device-to-device copies for the others
+    group.camera_set(p.projector_type, p.camera)
+    group.render_begin(p.width, p.height)
+
+
+def test_group_of_one_is_the_single_gpu_path(scenes, cuda_ctx):
+    """world = 1: no NCCL, same window merge as ccu_render_merge - and bit-identical to it."""
+    from chunkyclplugin_b200 import native
+    p = scenes("terrain64")
+    want = _one_gpu_merge(cuda_ctx, p, 5, 3, 0.25)
+    group = native.Group(devices=[0])
+    try:
+        assert (group.world, group.local_members) == (1, 1)
+        _load_group_scene(group, p)
+        sb = np.full(p.width * p.height * 3, 0.25, dtype=np.float64)
+        seeds = pass_seeds(5)
+        group.render_passes(seeds[:2])
+        group.render_passes(seeds[2:])       # a window may be rendered in several batches
+        assert group.render_merge(sb, 3) == 5
+        assert np.array_equal(sb, want)
+        assert group.render_merge(sb, 8) == 0   # empty window: nothing merged
+        group.render_end()
+    finally:
+        group.close()
+
+
+@pytest.mark.parametrize("n_passes", [6, 7])
+def test_two_gpu_group_matches_one_gpu(n_passes, scenes, cuda_ctx):
+    """One process, two GPUs (ncclCommInitAll): replicated scene, striped passes, reduce-scatter, per-GPU share merge.
+    7 passes = unequal per-GPU counts (window sums are scaled on the device), 6 = equal (folded into the merge weight)."""
+    if _n_gpus() < 2:
+        pytest.skip("NEEDS 2 GPUs - the 2-GPU group path is not exercised on this box")
+    from chunkyclplugin_b200 import native
+    p = scenes("terrain64")
+    want = _one_gpu_merge(cuda_ctx, p, n_passes, 3, 0.25)
+    group = native.Group(devices=[0, 1])
+    try:
+        assert (group.world, group.local_members) == (2, 2)
+        _load_group_scene(group, p)
+        sb = np.full(p.width * p.height * 3, 0.25, dtype=np.float64)
+        group.render_passes(pass_seeds(n_passes))
+        group.render_sync()
+        assert group.render_merge(sb, 3) == n_passes
+        render_ms, reduce_ms = group.last_ms()
+        assert render_ms > 0 and reduce_ms > 0
+        assert np.allclose(sb, want, rtol=2e-6, atol=1e-7)
+        # second window into the same buffer
+        group.render_passes(pass_seeds(n_passes + 4)[n_passes:])
+        assert group.render_merge(sb, 3 + n_passes) == 4
+        group.render_end()
+    finally:
+        group.close()
+    assert np.isfinite(sb).all() and sb.max() > 0
+
+
+def _worker(rank, world, port, n_passes, shm_name, n_doubles):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)       # only carries the NCCL id and the barriers
     try:
         from chunkyclplugin_b200 import native, scenes as S
-        from chunkyclplugin_b200.javarandom import pass_seeds
-        from chunkyclplugin_b200.multigpu import SampleParallelRenderer
-        from conftest import load_scene
+        from chunkyclplugin_b200.multigpu import SampleParallelRenderer, SharedSampleBuffer, join_process_group
         p = S.terrain_scene(64, 160, 90, seed=7)
         ctx = native.Context(rank)
         load_scene(ctx, p)
-        spr = SampleParallelRenderer(ctx, rank, world)
-        sb = np.full(p.width * p.height * 3, 0.25, dtype=np.float64) if rank == 0 else None
-        total = spr.render_and_merge(pass_seeds(n_passes), sb, sample_spp=3)
+        ctx.render_end()
+        group = join_process_group(ctx, rank, world)
+        group.camera_set(p.projector_type, p.camera)
+        group.render_begin(p.width, p.height)
+        sb = SharedSampleBuffer(n_doubles, name=shm_name, create=False)
+        spr = SampleParallelRenderer(group)
+        total = spr.render_and_merge(pass_seeds(n_passes), sb.array, 3)   # every rank merges its share into shared memory
         assert total == n_passes
-        if rank == 0:
-            np.save(out_path, sb)
+        dist.barrier()
+        group.render_end()
+        group.close()
         ctx.close()
+        sb.close()
     finally:
         dist.destroy_process_group()
 
 
-def test_two_gpu_window_merged_into_the_host_sample_buffer(tmp_path, scenes, cuda_ctx):
-    """render_and_merge: 2 ranks render, NCCL reduce, rank 0 merges with passSpp = all passes (java :167-173)."""
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def test_one_process_per_gpu_merges_into_shared_memory(scenes, cuda_ctx):
+    """torchrun shape: ccu_group_join on every rank, the sample buffer in shared memory."""
+    if _n_gpus() < 2:
+        pytest.skip("NEEDS 2 GPUs - the one-process-per-GPU group path is not exercised on this box")
     import torch.multiprocessing as mp
-    from chunkyclplugin_b200.javarandom import pass_seeds
-    from conftest import load_scene
-    n_passes = 6
-    out_path = str(tmp_path / "merged.npy")
-    mp.spawn(_worker_merge, args=(2, _free_port(), n_passes, out_path), nprocs=2, join=True)
-    merged = np.load(out_path)
+    from chunkyclplugin_b200.multigpu import SharedSampleBuffer
     p = scenes("terrain64")
-    load_scene(cuda_ctx, p)
-    cuda_ctx.render_passes(pass_seeds(n_passes))
-    one, _ = cuda_ctx.render_read()
-    want = (0.25 * 3 + one.astype(np.float64) * n_passes) / (3 + n_passes)
-    assert np.allclose(merged, want, rtol=2e-6, atol=1e-7)
+    n_passes = 6
+    want = _one_gpu_merge(cuda_ctx, p, n_passes, 3, 0.25)
+    sb = SharedSampleBuffer(p.width * p.height * 3)
+    try:
+        sb.array.fill(0.25)
+        mp.spawn(_worker, args=(2, _free_port(), n_passes, sb.name, sb.array.size), nprocs=2, join=True)
+        assert np.allclose(sb.array, want, rtol=2e-6, atol=1e-7)
+    finally:
+        sb.close()

@@ -33,10 +33,10 @@ def test_first_hit_bit_exact(name, scenes, cuda_ctx):
     assert (ref["kind"] > 0).any()
 
 
-@pytest.mark.parametrize("kernel", [4, 2, 3, 1], ids=["queue", "pool", "wavefront", "megakernel"])
+@pytest.mark.parametrize("kernel", [4, 1], ids=["wavefront", "thread_per_pixel"])
 @pytest.mark.parametrize("name", ALL)
 def test_render_bit_exact(name, kernel, scenes, cuda_ctx):
-    """Both render kernels (persistent wavefront = default, thread-per-pixel megakernel) against the oracle."""
+    """Both render kernels (persistent wavefront = default, thread-per-pixel cross-check) against the oracle."""
     import oracle
     p = scenes(name)
     load_scene(cuda_ctx, p)

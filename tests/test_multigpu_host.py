@@ -13,7 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from chunkyclplugin_b200.javarandom import pass_seeds
-from chunkyclplugin_b200.multigpu import combine_windows, partition_passes
+from chunkyclplugin_b200.multigpu import combine_windows, partition_passes, share_bounds
 
 
 def test_partition_is_a_round_robin_cover():
@@ -23,6 +23,25 @@ def test_partition_is_a_round_robin_cover():
         assert sorted(sum(parts, [])) == sorted(seeds)
         assert parts[0][:2] == [seeds[0], seeds[world]] if len(seeds) > world else True
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_partition_continues_through_a_window():
+    """A window rendered in several batches keeps the global pass numbering (ccu_group_render_passes)."""
+    seeds = pass_seeds(10)
+    for world in (2, 3, 8):
+        for r in range(world):
+            whole = partition_passes(seeds, r, world)
+            split = partition_passes(seeds[:3], r, world) + partition_passes(seeds[3:], r, world, first_pass=3)
+            assert whole == split
+
+
+def test_share_bounds_tile_the_buffer():
+    for n in (1, 3 * 75 * 41, 3 * 1920 * 1080, 3 * 3840 * 2160):
+        for world in (1, 2, 4, 8):
+            b = [share_bounds(n, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            assert all((hi - lo) % 256 == 0 for lo, hi in b[:-1] if hi < n)
 
 
 def test_combine_single_process_is_identity_mean():
