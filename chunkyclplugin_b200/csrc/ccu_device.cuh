@@ -34,6 +34,16 @@ struct DScene {
     const int *__restrict__ quad_models;
     const int *__restrict__ aabb_models;
     const int *__restrict__ mat_palette;
+    // 16-byte-vectorised palettes built at commit (use_recs): block_rec[2 * b] = {type, model ref, material flags, tint},
+    // block_rec[2 * b + 1] = {texSize, texLocation / ARGB, emittance, spec} for palette position b (a full-cube block is ONE
+    // 32-byte record: entry and material fused); mat_rec[2 * (ptr / 6)] the same six material words for everything else;
+    // quad_rec / aabb_rec: {count, 0, 0, 0} followed by one 64-byte record per quad (15 words + pad) / box (13 words + pad),
+    // referenced from block_rec in units of 16 bytes
+    const int4 *__restrict__ block_rec;
+    const int4 *__restrict__ mat_rec;
+    const int4 *__restrict__ quad_rec;
+    const int4 *__restrict__ aabb_rec;
+    int use_recs;
     const int *__restrict__ world_bvh;
     const int *__restrict__ actor_bvh;
     const int *__restrict__ trigs;
@@ -156,9 +166,9 @@ __device__ __forceinline__ float4 sky_read(const DScene &s, float cs, float ct) 
 // ------------------------------------------------------------------------------------------------------
 // material.h:31-82
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool material_sample(const DScene &s, int material, Surf &rec, float u, float v) {
-    const int *m = s.mat_palette + material;
-    uint32_t flags = __ldg(m), tint = __ldg(m + 1), tex_size = __ldg(m + 2), col = __ldg(m + 3), normal_emittance = __ldg(m + 4);
+// the material words {flags, tint, texSize, texLocation / ARGB, emittance} evaluated at (u, v)
+__device__ __forceinline__ bool material_eval(const DScene &s, uint32_t flags, uint32_t tint, uint32_t tex_size, uint32_t col, uint32_t normal_emittance,
+                                              Surf &rec, float u, float v) {
     float4 color;
     if (flags & 4u) color = atlas_read_uv(s, u, v, (int)col, (int)tex_size);
     else color = color_from_argb(col);
@@ -173,6 +183,17 @@ __device__ __forceinline__ bool material_sample(const DScene &s, int material, S
     if (flags & 2u) rec.emittance = atlas_read_uv(s, u, v, (int)normal_emittance, (int)tex_size).w;
     else rec.emittance = (float)((double)(normal_emittance & 0xFF) / 255.0);   // double literal in the reference (material.h:79)
     return true;
+}
+// Material_get + Material_sample for material pointer `material` (an int offset into matPalette, 6 words per material):
+// two 16-byte loads from the commit-time records, or the reference's own array for a pointer that is not on a record
+__device__ __forceinline__ bool material_sample(const DScene &s, int material, Surf &rec, float u, float v) {
+    const int idx = material / 6;
+    if (s.use_recs && material >= 0 && idx * 6 == material) {
+        const int4 a = __ldg(s.mat_rec + 2 * idx), b = __ldg(s.mat_rec + 2 * idx + 1);
+        return material_eval(s, (uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, rec, u, v);
+    }
+    const int *m = s.mat_palette + material;
+    return material_eval(s, __ldg(m), __ldg(m + 1), __ldg(m + 2), __ldg(m + 3), __ldg(m + 4), rec, u, v);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -223,15 +244,16 @@ __device__ __forceinline__ float box_full(const Box &b, float3 origin, float3 di
 }
 
 // primitives.h:200-260.  +z face: the reference reads an uninitialised material; defined as 0 / flags 0.
-__device__ __forceinline__ float textured_box(const int *model, float distance, float3 origin, float3 dir, float3 inv,
+// w[0..12]: the box's 13 words (PackedAabb.java:75-102)
+__device__ __forceinline__ float textured_box(const int *w, float distance, float3 origin, float3 dir, float3 inv,
                                               float3 &normal, float &u, float &v, int &material) {
-    Box b = {i2f(__ldg(model + 0)), i2f(__ldg(model + 1)), i2f(__ldg(model + 2)), i2f(__ldg(model + 3)), i2f(__ldg(model + 4)), i2f(__ldg(model + 5))};
+    Box b = {i2f(w[0]), i2f(w[1]), i2f(w[2]), i2f(w[3]), i2f(w[4]), i2f(w[5])};
     float3 n = f3(0, 0, 0);
     float tu = 0, tv = 0;
     float dist = box_full<true>(b, origin, dir, inv, n, tu, tv);
     if (dist >= distance || dist < -CCU_EPS) return nanf_();
     if (is_nan(dist)) return nanf_();
-    int bflags = __ldg(model + 6);
+    int bflags = w[6];
     int slot = -1, flags = 0;
     if (n.z == -1.0f) { slot = 7; flags = bflags; }
     if (n.x == 1.0f) { slot = 8; flags = bflags >> 4; }
@@ -243,16 +265,19 @@ __device__ __forceinline__ float textured_box(const int *model, float distance, 
     if (flags & 4) tu = 1.0f - tu;
     if (flags & 2) tv = 1.0f - tv;
     if (flags & 1) { float t = tu; tu = tv; tv = t; }
-    material = slot < 0 ? 0 : __ldg(model + slot);
+    material = 0;
+#pragma unroll
+    for (int k = 7; k < 13; k++) if (slot == k) material = w[k];
     normal = n; u = tu; v = tv;
     return dist;
 }
 
 // primitives.h:274-319
+// q[0..12]: the quad's first 13 words (PackedQuad.java:41-66)
 __device__ __forceinline__ float quad_hit(const int *q, float distance, float3 origin, float3 dir, float3 &normal, float &u, float &v) {
-    float3 qo = f3(i2f(__ldg(q + 0)), i2f(__ldg(q + 1)), i2f(__ldg(q + 2)));
-    float3 xv = f3(i2f(__ldg(q + 3)), i2f(__ldg(q + 4)), i2f(__ldg(q + 5)));
-    float3 yv = f3(i2f(__ldg(q + 6)), i2f(__ldg(q + 7)), i2f(__ldg(q + 8)));
+    float3 qo = f3(i2f(q[0]), i2f(q[1]), i2f(q[2]));
+    float3 xv = f3(i2f(q[3]), i2f(q[4]), i2f(q[5]));
+    float3 yv = f3(i2f(q[6]), i2f(q[7]), i2f(q[8]));
     float3 n = normalize3(cross3(xv, yv));
     float denom = dot3(dir, n);
     if (denom < -CCU_EPS) {
@@ -262,8 +287,8 @@ __device__ __forceinline__ float quad_hit(const int *q, float distance, float3 o
             float uu = dot3(pt, xv) / dot3(xv, xv);
             float vv = dot3(pt, yv) / dot3(yv, yv);
             if (uu >= 0 && uu <= 1 && vv >= 0 && vv <= 1) {
-                u = i2f(__ldg(q + 9)) + (uu * i2f(__ldg(q + 10)));
-                v = i2f(__ldg(q + 11)) + (vv * i2f(__ldg(q + 12)));
+                u = i2f(q[9]) + (uu * i2f(q[10]));
+                v = i2f(q[11]) + (vv * i2f(q[12]));
                 normal = n;
                 return t;
             }
@@ -324,19 +349,38 @@ static __device__ __noinline__ ModelHit intersect_model_block(const DScene &s, i
     float u = 0, v = 0;
     bool hit = false;
     float dist = inff_();
+    // model_ptr: offset into the reference's int arrays, or (use_recs) into the 16-byte record arrays in units of 16 bytes
+    int w[16];
     if (model_type == 2) {
-        int boxes = __ldg(s.aabb_models + model_ptr);
+        const int boxes = s.use_recs ? __ldg(s.aabb_rec + model_ptr).x : __ldg(s.aabb_models + model_ptr);
         for (int i = 0; i < boxes; i++) {
+            if (s.use_recs) {
+                const int4 *r = s.aabb_rec + model_ptr + 1 + 4 * i;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const int4 t = __ldg(r + k); w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
+            } else {
+                const int *m = s.aabb_models + model_ptr + 1 + i * 13;
+#pragma unroll
+                for (int k = 0; k < 13; k++) w[k] = __ldg(m + k);
+            }
             int material = 0;
-            float t = textured_box(s.aabb_models + model_ptr + 1 + i * 13, dist, norm_origin, direction, inv, normal, u, v, material);
+            float t = textured_box(w, dist, norm_origin, direction, inv, normal, u, v, material);
             if (!is_nan(t) && material_sample(s, material, out.surf, u, v)) { out.surf.normal = normal; dist = t; hit = true; }
         }
     } else {
-        int quads = __ldg(s.quad_models + model_ptr);
+        const int quads = s.use_recs ? __ldg(s.quad_rec + model_ptr).x : __ldg(s.quad_models + model_ptr);
         for (int i = 0; i < quads; i++) {
-            const int *q = s.quad_models + model_ptr + 1 + i * 15;
-            float t = quad_hit(q, dist, norm_origin, direction, normal, u, v);
-            if (!is_nan(t) && material_sample(s, __ldg(q + 13), out.surf, u, v)) { out.surf.normal = normal; dist = t; hit = true; }
+            if (s.use_recs) {
+                const int4 *r = s.quad_rec + model_ptr + 1 + 4 * i;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const int4 t = __ldg(r + k); w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
+            } else {
+                const int *q = s.quad_models + model_ptr + 1 + i * 15;
+#pragma unroll
+                for (int k = 0; k < 14; k++) w[k] = __ldg(q + k);
+            }
+            float t = quad_hit(w, dist, norm_origin, direction, normal, u, v);
+            if (!is_nan(t) && material_sample(s, w[13], out.surf, u, v)) { out.surf.normal = normal; dist = t; hit = true; }
         }
     }
     out.dist = hit ? dist : nanf_();
@@ -350,7 +394,14 @@ __device__ __forceinline__ float intersect_block(const DScene &s, int block, int
                                                  float3 direction, float3 inv) {
     if (block == CCU_ANY_TYPE) return nanf_();
     if (block < 0 || block + 1 >= s.block_palette_len) return nanf_();   // out-of-palette leaf (undefined in the reference)
-    int model_type = __ldg(s.block_palette + block), model_ptr = __ldg(s.block_palette + block + 1);
+    int model_type, model_ptr;
+    int4 r0 = make_int4(0, 0, 0, 0);
+    if (s.use_recs) {
+        r0 = __ldg(s.block_rec + 2 * block);
+        model_type = r0.x; model_ptr = r0.y;
+    } else {
+        model_type = __ldg(s.block_palette + block); model_ptr = __ldg(s.block_palette + block + 1);
+    }
     float3 norm_origin = (pos - direction * CCU_OFFSET) - f3((float)bx, (float)by, (float)bz);
     if (model_type == 1) {
         Box unit = {0, 1, 0, 1, 0, 1};
@@ -360,7 +411,11 @@ __device__ __forceinline__ float intersect_block(const DScene &s, int block, int
         float dist = box_full<false>(unit, norm_origin, pos, inv, normal, u, v);
         if (is_nan(dist)) return nanf_();
         Surf tmp;
-        if (!material_sample(s, model_ptr, tmp, u, v)) return nanf_();
+        if (s.use_recs) {
+            // the full cube's material travels with its palette entry
+            const int4 r1 = __ldg(s.block_rec + 2 * block + 1);
+            if (!material_eval(s, (uint32_t)r0.z, (uint32_t)r0.w, (uint32_t)r1.x, (uint32_t)r1.y, (uint32_t)r1.z, tmp, u, v)) return nanf_();
+        } else if (!material_sample(s, model_ptr, tmp, u, v)) return nanf_();
         surf.color = tmp.color;
         surf.emittance = tmp.emittance;
         surf.normal = normal;

@@ -101,7 +101,9 @@ struct ccu_ctx {
     ccu_host::DevBuf<unsigned> top, wide;                       // value-carrying octree layout
     ccu_host::DevBuf<unsigned> air_top, air_wide, air_bricks;   // march layout (ccu_march.cuh)
     ccu_host::DevBuf<int> world_rec, actor_rec, tris2;          // BVH stage layout (ccu_queue.cuh)
-    ccu_host::DevBuf<int> cube_rec;                             // fused block + material records of full-cube blocks
+    ccu_host::DevBuf<int> block_rec, mat_rec, quad_rec, aabb_rec;   // 16-byte-vectorised palettes (DScene::block_rec ...)
+    std::vector<int> quad_host, aabb_host;
+    int use_recs = 0;
     int world_root = 0, actor_root = 0, use_bvh2 = 0, use_air = 0, air_deep = 0;
     int cell_level = 0, top_log2 = 0, use_wide = 0, air_cell_level = 4, air_top_log2 = 0;
     double commit_ms = 0;                                       // host time of the last ccu_scene_commit

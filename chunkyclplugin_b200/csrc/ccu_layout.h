@@ -282,4 +282,62 @@ WideLayout build_wide_layout(const int *tree, size_t n, int depth) {
     if (b.wide.empty()) b.wide.assign(64, wide_leaf(0, 0, b.ok));
     return b;
 }
+
+// 16-byte-vectorised palettes (DScene::block_rec / mat_rec / quad_rec / aabb_rec): the reference's scalar int[] palettes
+// (PackedBlock.java:79-85, PackedMaterial.java:74-100, PackedQuad.java:41-66, PackedAabb.java:75-102) re-laid out so that a
+// block test reads whole records with 128-bit loads.  A block-palette position whose entry cannot be translated (model pointer
+// outside its palette) keeps type 0x7FFFFFFF, which no branch of intersect_block accepts - the same miss the reference's
+// out-of-range read would most likely produce, but defined.
+struct PaletteRecs {
+    std::vector<int> block, mat, quad, aabb;
+    bool ok = true;
+};
+
+inline PaletteRecs build_palette_recs(const std::vector<int> &bp, const std::vector<int> &mp, const int *quads, size_t n_quads,
+                                      const int *aabbs, size_t n_aabbs) {
+    PaletteRecs r;
+    const size_t n_mat = mp.size() / 6;
+    r.mat.assign(std::max<size_t>(n_mat, 1) * 8, 0);
+    for (size_t i = 0; i < n_mat; i++)
+        for (int k = 0; k < 6; k++) r.mat[i * 8 + k] = mp[i * 6 + k];
+    std::unordered_map<int, int> quad_at, aabb_at;     // model pointer -> offset in units of 16 bytes
+    auto model = [&](const int *src, size_t n, int ptr, int words, std::vector<int> &dst, std::unordered_map<int, int> &at, int &out) {
+        auto it = at.find(ptr);
+        if (it != at.end()) { out = it->second; return true; }
+        if (ptr < 0 || (size_t)ptr >= n) return false;
+        const int count = src[ptr];
+        if (count < 0 || (size_t)ptr + 1 + (size_t)count * words > n) return false;
+        out = (int)(dst.size() / 4);
+        dst.push_back(count); dst.push_back(0); dst.push_back(0); dst.push_back(0);
+        for (int i = 0; i < count; i++) {
+            for (int k = 0; k < 16; k++) dst.push_back(k < words ? src[(size_t)ptr + 1 + (size_t)i * words + k] : 0);
+        }
+        at.emplace(ptr, out);
+        return true;
+    };
+    const size_t n_pos = bp.size() >= 2 ? bp.size() - 1 : 0;
+    r.block.assign(std::max<size_t>(n_pos, 1) * 8, 0);
+    for (size_t b = 0; b < n_pos; b++) {
+        int *rec = &r.block[b * 8];
+        const int type = bp[b], ptr = bp[b + 1];
+        rec[0] = type;
+        rec[1] = ptr;
+        if (type == 1) {
+            // full cube: the six material words travel with the entry
+            if (ptr >= 0 && (size_t)ptr + 5 < mp.size()) {
+                for (int k = 0; k < 6; k++) rec[2 + k] = mp[(size_t)ptr + k];
+            } else {
+                rec[0] = 0x7FFFFFFF;
+            }
+        } else if (type == 2) {
+            if (!model(aabbs, n_aabbs, ptr, 13, r.aabb, aabb_at, rec[1])) rec[0] = 0x7FFFFFFF;
+        } else if (type == 3) {
+            if (!model(quads, n_quads, ptr, 15, r.quad, quad_at, rec[1])) rec[0] = 0x7FFFFFFF;
+        }
+    }
+    if (r.quad.empty()) r.quad.assign(4, 0);
+    if (r.aabb.empty()) r.aabb.assign(4, 0);
+    return r;
+}
+
 }  // namespace

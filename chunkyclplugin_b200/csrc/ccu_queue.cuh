@@ -70,11 +70,19 @@ constexpr uint32_t QM_NEEDPIX = 1u << 25;    // the slot holds no pixel (initial
 constexpr uint32_t QM_HIT = 1u << 26;        // BVH / SHADE stages: the ray has a hit (QF_H* valid)
 
 constexpr int Q_TOP_WORDS = 4096;            // top tables up to 16^3 cells are staged in shared memory
+// BVH stage: the first Q_STACK entries of a walk's traversal stack (bvh.h:38 nodesToVisit[64]) live in shared memory, one
+// word per entry and lane (entry k of lane l of warp w at word (k * Q_WARPS + w) * 32 + l: bank = lane, conflict free);
+// deeper entries, which a reasonable BVH never needs, go to local memory.
+#ifndef CCU_Q_STACK
+#define CCU_Q_STACK 20
+#endif
+constexpr int Q_STACK = CCU_Q_STACK;
+constexpr int Q_STACK_WORDS = Q_STACK * Q_WARPS * 32;
 __host__ __device__ constexpr int q_fields(bool bvh) { return bvh ? (int)QF_COUNT_BVH : (int)QF_COUNT; }
 __host__ __device__ constexpr int q_stages(bool bvh) { return bvh ? (int)QS_COUNT_BVH : (int)QS_COUNT; }
 __host__ __device__ constexpr int q_mask_words(bool bvh) { return q_stages(bvh) * Q_MW * 32; }
 // slot fields + work masks + control words (live, tile lock / base / used) [+ the staged top table]
-__host__ __device__ constexpr int q_smem_bytes(bool bvh, bool tops) { return (q_fields(bvh) * Q_SLOTS + q_mask_words(bvh) + 32 + (tops ? Q_TOP_WORDS : 0)) * 4; }
+__host__ __device__ constexpr int q_smem_bytes(bool bvh, bool tops) { return (q_fields(bvh) * Q_SLOTS + q_mask_words(bvh) + 32 + (tops ? Q_TOP_WORDS : 0) + (bvh ? Q_STACK_WORDS : 0)) * 4; }
 
 #ifdef CCU_Q_STATS
 // debug counters (build with -DCCU_Q_STATS): [2*st] = executions of stage st, [2*st+1] = lanes that had a slot;
@@ -416,14 +424,16 @@ __device__ __forceinline__ void bvh_next_phase(const DScene &s, BvhWalk &b) {
     }
 }
 
-__device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsigned *mask, int lane, int refill_min, int leaf_min) {
+__device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsigned *mask, int *stk, int lane, int refill_min, int leaf_min) {
     const unsigned full = 0xffffffffu;
     int cur = -1;
     BvhWalk b;
     b.o = b.d = b.inv = f3(0, 0, 0);
     b.dist = 0; b.any = false; b.ref = 0; b.sp = 0; b.phase = 2;
     b.hit.normal = f3(0, 0, 0); b.hit.color = make_float4(0, 0, 0, 0); b.hit.emittance = 0;
-    int stack[64];      // bvh.h:38
+    // bvh.h:38: entry k < Q_STACK at stk[k * Q_WARPS * 32] (stk already points at this lane's column), the rest in local memory
+    int deep[64 - Q_STACK];
+    constexpr int SK = Q_WARPS * 32;
     int n_done = 0, n_fly = 0;
     unsigned iter = 0;
     for (;;) {
@@ -501,17 +511,22 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
                 else b.ref = right;
             } else if (miss2) {
                 b.ref = left;
-            } else if (t1 < t2) {
-                stack[b.sp++] = right;
-                b.ref = left;
             } else {
-                stack[b.sp++] = left;
-                b.ref = right;
+                const bool near_left = t1 < t2;
+                const int far = near_left ? right : left;
+                if (b.sp < Q_STACK) stk[b.sp * SK] = far;
+                else deep[b.sp - Q_STACK] = far;
+                b.sp++;
+                b.ref = near_left ? left : right;
             }
         }
         if (pop) {
-            if (b.sp == 0) bvh_next_phase(s, b);
-            else b.ref = stack[--b.sp];
+            if (b.sp == 0) {
+                bvh_next_phase(s, b);
+            } else {
+                b.sp--;
+                b.ref = b.sp < Q_STACK ? stk[b.sp * SK] : deep[b.sp - Q_STACK];
+            }
         }
         n_fly = __popc(__ballot_sync(full, cur >= 0 && b.phase < 2));
         n_done = __popc(__ballot_sync(full, cur >= 0 && b.phase >= 2));
@@ -641,6 +656,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
     unsigned *mask = q_mem + q_fields(HAS_BVH) * Q_SLOTS;
     int *live = reinterpret_cast<int *>(mask + MASK_WORDS);
     unsigned *top_s = mask + MASK_WORDS + 32;
+    int *stk = reinterpret_cast<int *>(top_s + (LAY == 0 ? Q_TOP_WORDS : 0)) + threadIdx.x;   // HAS_BVH only: this lane's stack column
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
 
@@ -686,7 +702,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
             case QS_BLOCK:
             case QS_EXIT: q_stage_resolve<HAS_BVH>(s, F, mask, lane, best == QS_BLOCK); break;
             case QS_END: q_stage_end(s, qp.w, F, mask, live, lane); break;
-            case QS_BVH: QSTAT(16, 1); if (HAS_BVH) q_stage_bvh(s, F, mask, lane, qp.refill_min, qp.leaf_min); break;
+            case QS_BVH: QSTAT(16, 1); if (HAS_BVH) q_stage_bvh(s, F, mask, stk, lane, qp.refill_min, qp.leaf_min); break;
             default: if (HAS_BVH) q_stage_shade(s, F, mask, lane); break;
         }
         __syncwarp();

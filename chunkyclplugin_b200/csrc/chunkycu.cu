@@ -274,6 +274,11 @@ void fill_scene(ccu_ctx *c) {
     s.quad_models = c->quad_models.p;
     s.aabb_models = c->aabb_models.p;
     s.mat_palette = c->mat_palette.p;
+    s.block_rec = reinterpret_cast<const int4 *>(c->block_rec.p);
+    s.mat_rec = reinterpret_cast<const int4 *>(c->mat_rec.p);
+    s.quad_rec = reinterpret_cast<const int4 *>(c->quad_rec.p);
+    s.aabb_rec = reinterpret_cast<const int4 *>(c->aabb_rec.p);
+    s.use_recs = c->use_recs;
     s.world_bvh = c->world_bvh.p;
     s.actor_bvh = c->actor_bvh.p;
     s.trigs = c->trigs.p;
@@ -433,13 +438,14 @@ int replicate_scene(ccu_ctx *src, ccu_ctx *dst) {
     int rc = CCU_OK;
 #define CP(m) if (rc == CCU_OK) rc = copy_buf(src, dst, &ccu_ctx::m)
     CP(tree); CP(block_palette); CP(quad_models); CP(aabb_models); CP(mat_palette); CP(trigs); CP(world_bvh); CP(actor_bvh); CP(sun_words);
-    CP(top); CP(wide); CP(air_top); CP(air_wide); CP(air_bricks); CP(world_rec); CP(actor_rec); CP(tris2); CP(cube_rec); CP(atlas); CP(sky); CP(sun_basis);
+    CP(top); CP(wide); CP(air_top); CP(air_wide); CP(air_bricks); CP(world_rec); CP(actor_rec); CP(tris2); CP(block_rec); CP(mat_rec); CP(quad_rec); CP(aabb_rec); CP(atlas); CP(sky); CP(sun_basis);
 #undef CP
     if (rc != CCU_OK) return rc;
     dst->world_host = src->world_host.size() >= 7 ? std::vector<int>(src->world_host.begin(), src->world_host.begin() + 7) : src->world_host;
     dst->actor_host = src->actor_host.size() >= 7 ? std::vector<int>(src->actor_host.begin(), src->actor_host.begin() + 7) : src->actor_host;
     dst->tree_host.clear(); dst->trigs_host.clear(); dst->block_host.clear(); dst->mat_host.clear();
     dst->world_root = src->world_root; dst->actor_root = src->actor_root; dst->use_bvh2 = src->use_bvh2; dst->use_air = src->use_air;
+    dst->use_recs = src->use_recs;
     dst->air_deep = src->air_deep; dst->cell_level = src->cell_level; dst->top_log2 = src->top_log2; dst->use_wide = src->use_wide;
     dst->air_cell_level = src->air_cell_level; dst->air_top_log2 = src->air_top_log2;
     dst->atlas_w = src->atlas_w; dst->atlas_h = src->atlas_h; dst->atlas_layers = src->atlas_layers;
@@ -546,7 +552,7 @@ int ccu_ctx_destroy(ccu_ctx *c) {
         cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copy_stream);
         c->tree.release(); c->top.release(); c->wide.release(); c->air_top.release(); c->air_wide.release(); c->air_bricks.release();
-        c->world_rec.release(); c->actor_rec.release(); c->tris2.release(); c->cube_rec.release(); c->block_palette.release();
+        c->world_rec.release(); c->actor_rec.release(); c->tris2.release(); c->block_rec.release(); c->mat_rec.release(); c->quad_rec.release(); c->aabb_rec.release(); c->block_palette.release();
         c->quad_models.release(); c->aabb_models.release(); c->mat_palette.release(); c->trigs.release(); c->world_bvh.release();
         c->actor_bvh.release(); c->sun_words.release(); c->atlas.release(); c->sky.release(); c->rays[0].release(); c->rays[1].release();
         c->sun_basis.release();
@@ -578,7 +584,7 @@ int ccu_scene_begin(ccu_ctx *c) {
     cudaStreamSynchronize(c->stream);
     c->committed = false;
     c->quad_models.release(); c->aabb_models.release(); c->trigs.release(); c->world_bvh.release(); c->actor_bvh.release();
-    c->world_host.clear(); c->actor_host.clear(); c->trigs_host.clear();
+    c->world_host.clear(); c->actor_host.clear(); c->trigs_host.clear(); c->quad_host.clear(); c->aabb_host.clear();
     c->have_octree = c->have_blocks = c->have_mats = c->have_atlas = c->have_sky = c->have_sun = false;
     return CCU_OK;
 }
@@ -596,10 +602,10 @@ int ccu_scene_set_block_palette(ccu_ctx *c, const int32_t *w, int64_t n) {
     return upload_words(c, &ccu_ctx::block_palette, w, n, "ccu_scene_set_block_palette", [&] { c->block_host.assign(w, w + n); c->have_blocks = true; });
 }
 int ccu_scene_set_quad_models(ccu_ctx *c, const int32_t *w, int64_t n) {
-    return upload_words(c, &ccu_ctx::quad_models, w, n, "ccu_scene_set_quad_models", [] {});
+    return upload_words(c, &ccu_ctx::quad_models, w, n, "ccu_scene_set_quad_models", [&] { c->quad_host.assign(w, w + n); });
 }
 int ccu_scene_set_aabb_models(ccu_ctx *c, const int32_t *w, int64_t n) {
-    return upload_words(c, &ccu_ctx::aabb_models, w, n, "ccu_scene_set_aabb_models", [] {});
+    return upload_words(c, &ccu_ctx::aabb_models, w, n, "ccu_scene_set_aabb_models", [&] { c->aabb_host.assign(w, w + n); });
 }
 int ccu_scene_set_material_palette(ccu_ctx *c, const int32_t *w, int64_t n) {
     return upload_words(c, &ccu_ctx::mat_palette, w, n, "ccu_scene_set_material_palette", [&] { c->mat_host.assign(w, w + n); c->have_mats = true; });
@@ -699,8 +705,8 @@ int ccu_scene_commit(ccu_ctx *c) {
     const auto t0 = std::chrono::steady_clock::now();
     // absent optional palettes behave as the reference's single zero word / EMPTY_NODE
     int zero = 0;
-    if (!c->quad_models.p) CU(c->quad_models.upload(&zero, 0, c->stream));
-    if (!c->aabb_models.p) CU(c->aabb_models.upload(&zero, 0, c->stream));
+    if (!c->quad_models.p) { CU(c->quad_models.upload(&zero, 0, c->stream)); c->quad_host.clear(); }
+    if (!c->aabb_models.p) { CU(c->aabb_models.upload(&zero, 0, c->stream)); c->aabb_host.clear(); }
     if (!c->trigs.p) { CU(c->trigs.upload(&zero, 0, c->stream)); c->trigs_host.clear(); }
     if (!c->world_bvh.p) { CU(c->world_bvh.upload(&zero, 0, c->stream)); c->world_host.clear(); }
     if (!c->actor_bvh.p) { CU(c->actor_bvh.upload(&zero, 0, c->stream)); c->actor_host.clear(); }
@@ -722,6 +728,15 @@ int ccu_scene_commit(ccu_ctx *c) {
         CU(c->air_top.upload(al.top.data(), al.top.size(), c->stream));
         CU(c->air_wide.upload(al.wide.data(), al.wide.size(), c->stream));
         CU(c->air_bricks.upload(al.bricks.data(), al.bricks.size(), c->stream));
+    }
+    // 16-byte-vectorised block / material / model palettes
+    {
+        PaletteRecs pr = build_palette_recs(c->block_host, c->mat_host, c->quad_host.data(), c->quad_host.size(), c->aabb_host.data(), c->aabb_host.size());
+        c->use_recs = getenv("CCU_NO_RECS") == nullptr ? 1 : 0;
+        CU(c->block_rec.upload(pr.block.data(), pr.block.size(), c->stream));
+        CU(c->mat_rec.upload(pr.mat.data(), pr.mat.size(), c->stream));
+        CU(c->quad_rec.upload(pr.quad.data(), pr.quad.size(), c->stream));
+        CU(c->aabb_rec.upload(pr.aabb.data(), pr.aabb.size(), c->stream));
     }
     // BVH stage layout (pair records + aligned triangle blocks); a BVH it cannot hold (malformed, or deeper than the 64 entries
     // of the reference's traversal stack, bvh.h:38) is rendered by the thread-per-pixel kernel on the reference's own arrays
@@ -1196,7 +1211,7 @@ int ccu_scene_device_bytes(ccu_ctx *c, int64_t *bytes) {
     if (!c || !bytes) return fail(CCU_EINVAL, "ccu_scene_device_bytes: null argument");
     std::lock_guard<std::mutex> lk(c->mu);
     *bytes = (int64_t)(c->tree.bytes() + c->top.bytes() + c->wide.bytes() + c->air_top.bytes() + c->air_wide.bytes() + c->air_bricks.bytes() +
-                       c->world_rec.bytes() + c->actor_rec.bytes() + c->tris2.bytes() + c->cube_rec.bytes() + c->block_palette.bytes() +
+                       c->world_rec.bytes() + c->actor_rec.bytes() + c->tris2.bytes() + c->block_rec.bytes() + c->mat_rec.bytes() + c->quad_rec.bytes() + c->aabb_rec.bytes() + c->block_palette.bytes() +
                        c->quad_models.bytes() + c->aabb_models.bytes() + c->mat_palette.bytes() + c->trigs.bytes() + c->world_bvh.bytes() +
                        c->actor_bvh.bytes() + c->atlas.bytes() + c->sky.bytes());
     return CCU_OK;

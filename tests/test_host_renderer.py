@@ -58,6 +58,7 @@ def test_post_render_callback_stops_rendering(scenes):
     from chunkyclplugin_b200.renderer import CudaPathTracingRenderer, CudaSceneLoader, RendererInstance
     p = scenes("terrain64")
     r = CudaPathTracingRenderer(CudaSceneLoader(RendererInstance.get(0)), passes_per_call=1)
+    r.CALLBACK_MS = 0.0            # poll after every call (the reference polls at most every 100 ms, OpenClPathTracingRenderer.java:153-157)
     calls = []
     r.setPostRender(lambda: calls.append(1) or len(calls) >= 3)
     mgr = _manager(p, 100)
