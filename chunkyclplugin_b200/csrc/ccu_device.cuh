@@ -5,6 +5,20 @@
 #pragma once
 #include "ccu_math.cuh"
 
+// march_begin_core is kept out of line (one copy instead of one per ray kind: measured -4 % on the wavefront kernel, whose
+// shading stages are limited by instruction fetch); -DCCU_INLINE_MARCH_BEGIN restores the inlined form.  CCU_NI_MATERIAL /
+// CCU_NI_MATH do the same for the material evaluation / math helpers (measured: no gain, off by default).
+#ifndef CCU_INLINE_MARCH_BEGIN
+#define CCU_MARCH_BEGIN_INLINE static __device__ __noinline__
+#else
+#define CCU_MARCH_BEGIN_INLINE __device__ __forceinline__
+#endif
+#ifdef CCU_NI_MATERIAL
+#define CCU_MATERIAL_INLINE static __device__ __noinline__
+#else
+#define CCU_MATERIAL_INLINE __device__ __forceinline__
+#endif
+
 namespace ccu {
 
 #define CCU_ANY_TYPE 0x7FFFFFFE   // block.h:32
@@ -107,10 +121,29 @@ __device__ __forceinline__ float4 color_from_argb(uint32_t argb) {   // utils.h:
     c.z = (float)(argb & 0xFF) / 256.0f;
     return c;
 }
+// Small read-only tables every kernel of this file stages in shared memory when it starts (stage_tables): the UNORM8 -> float
+// table, and a pointer to the sky texels - the wavefront kernel copies the sky table itself into its dynamic shared memory
+// (res^2 <= 16384 texels, 64 KiB) and points `sky` there, the thread-per-ray kernels leave it pointing at global memory.
+struct SmemTables {
+    float unorm[256];
+    const uchar4 *sky;
+};
+__device__ __forceinline__ SmemTables &smem_tables() {
+    __shared__ SmemTables t;
+    return t;
+}
+// cooperative; ends with a barrier.  sky_smem: where the kernel staged the sky texels (nullptr: read them from global memory)
+__device__ __forceinline__ void stage_tables(const DScene &s, const uchar4 *sky_smem) {
+    SmemTables &t = smem_tables();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) t.unorm[i] = __ldg(s.unorm + i);
+    if (threadIdx.x == 0) t.sky = sky_smem ? sky_smem : s.sky;
+    __syncthreads();
+}
 // RGBA8 UNORM -> float: byte / 255.0f, read from a 256-entry table holding exactly those IEEE quotients
-// (built once on the device by k_unorm_table), which replaces four divisions per texel by four loads.
+// (built once on the device by k_unorm_table), which replaces four divisions per texel by four shared-memory loads.
 __device__ __forceinline__ float4 unorm8(const DScene &s, uchar4 t) {
-    return make_float4(__ldg(s.unorm + t.x), __ldg(s.unorm + t.y), __ldg(s.unorm + t.z), __ldg(s.unorm + t.w));
+    const float *u = smem_tables().unorm;
+    return make_float4(u[t.x], u[t.y], u[t.z], u[t.w]);
 }
 // textureAtlas.h:10-16: nearest / clamp-to-edge / integer coordinates
 __device__ __forceinline__ float4 atlas_read_xy(const DScene &s, int x, int y, int location) {
@@ -150,10 +183,11 @@ __device__ __forceinline__ float4 sky_read(const DScene &s, float cs, float ct) 
     float a, b;
     sky_axis(cs, w, i0, i1, a);
     sky_axis(ct, w, j0, j1, b);
-    float4 t00 = unorm8(s, __ldg(s.sky + j0 * w + i0));
-    float4 t10 = unorm8(s, __ldg(s.sky + j0 * w + i1));
-    float4 t01 = unorm8(s, __ldg(s.sky + j1 * w + i0));
-    float4 t11 = unorm8(s, __ldg(s.sky + j1 * w + i1));
+    const uchar4 *sky = smem_tables().sky;      // shared memory (wavefront kernel, table staged) or global memory
+    float4 t00 = unorm8(s, sky[j0 * w + i0]);
+    float4 t10 = unorm8(s, sky[j0 * w + i1]);
+    float4 t01 = unorm8(s, sky[j1 * w + i0]);
+    float4 t11 = unorm8(s, sky[j1 * w + i1]);
     float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
     float4 r;
     r.x = ((w00 * t00.x + w10 * t10.x) + w01 * t01.x) + w11 * t11.x;
@@ -166,22 +200,37 @@ __device__ __forceinline__ float4 sky_read(const DScene &s, float cs, float ct) 
 // ------------------------------------------------------------------------------------------------------
 // material.h:31-82
 // ------------------------------------------------------------------------------------------------------
-// the material words {flags, tint, texSize, texLocation / ARGB, emittance} evaluated at (u, v)
-__device__ __forceinline__ bool material_eval(const DScene &s, uint32_t flags, uint32_t tint, uint32_t tex_size, uint32_t col, uint32_t normal_emittance,
-                                              Surf &rec, float u, float v) {
+// the material words {flags, tint, texSize, texLocation / ARGB, emittance} evaluated at (u, v); returned by value so that an
+// out-of-line copy (CCU_NI_MATERIAL) hands the result back in registers
+struct MatOut { float4 color; float emittance; int ok; };
+CCU_MATERIAL_INLINE MatOut material_eval_core(const DScene &s, uint32_t flags, uint32_t tint, uint32_t tex_size, uint32_t col, uint32_t normal_emittance,
+                                              float u, float v) {
+    MatOut out;
+    out.emittance = 0.0f;
+    out.ok = 0;
     float4 color;
     if (flags & 4u) color = atlas_read_uv(s, u, v, (int)col, (int)tex_size);
     else color = color_from_argb(col);
-    if (color.w > CCU_EPS) rec.color = color;
-    else return false;
+    out.color = color;
+    if (!(color.w > CCU_EPS)) return out;
     uint32_t tt = tint >> 24;
     if (tt == 0xFF || (tt >= 1 && tt <= 3)) {
         uint32_t argb = tt == 0xFF ? tint : (tt == 1 ? 0xFF71A74Du : (tt == 2 ? 0xFF8EB971u : 0xFF3F76E4u));
         float4 t = color_from_argb(argb);
-        rec.color.x *= t.x; rec.color.y *= t.y; rec.color.z *= t.z; rec.color.w *= t.w;
+        out.color.x *= t.x; out.color.y *= t.y; out.color.z *= t.z; out.color.w *= t.w;
     }
-    if (flags & 2u) rec.emittance = atlas_read_uv(s, u, v, (int)normal_emittance, (int)tex_size).w;
-    else rec.emittance = (float)((double)(normal_emittance & 0xFF) / 255.0);   // double literal in the reference (material.h:79)
+    if (flags & 2u) out.emittance = atlas_read_uv(s, u, v, (int)normal_emittance, (int)tex_size).w;
+    else out.emittance = (float)((double)(normal_emittance & 0xFF) / 255.0);   // double literal in the reference (material.h:79)
+    out.ok = 1;
+    return out;
+}
+// rec.color / rec.emittance are written only on success (material.h:50-54 rejects before storing)
+__device__ __forceinline__ bool material_eval(const DScene &s, uint32_t flags, uint32_t tint, uint32_t tex_size, uint32_t col, uint32_t normal_emittance,
+                                              Surf &rec, float u, float v) {
+    const MatOut m = material_eval_core(s, flags, tint, tex_size, col, normal_emittance, u, v);
+    if (!m.ok) return false;
+    rec.color = m.color;
+    rec.emittance = m.emittance;
     return true;
 }
 // Material_get + Material_sample for material pointer `material` (an int offset into matPalette, 6 words per material):
@@ -473,24 +522,34 @@ struct March {
     int steps;
 };
 
-// octree.h:43-64: returns false when the ray starts outside the octree cube and never enters it
-__device__ __forceinline__ bool march_begin(const DScene &s, March &m, float3 origin, float3 direction, float limit) {
-    m.o = origin;
-    m.d = direction;
-    m.inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
-    m.t = 0;
-    m.limit = limit;
-    m.steps = 0;
-    const int depth = s.depth;
+// octree.h:43-64: 1 / d, the distance to the octree cube for a ray that starts outside of it, and whether it enters at all.
+// Returned by value so that an out-of-line copy (CCU_NI_MARCH_BEGIN) hands the result back in registers.
+struct MarchStart { float3 inv; float t; int entered; };
+CCU_MARCH_BEGIN_INLINE MarchStart march_begin_core(int depth, float3 origin, float3 direction) {
+    MarchStart ms;
+    ms.inv = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+    ms.t = 0;
+    ms.entered = 1;
     int lx = f2i(floorf(origin.x)) >> depth, ly = f2i(floorf(origin.y)) >> depth, lz = f2i(floorf(origin.z)) >> depth;
     if ((lx | ly | lz) != 0) {
         float size = (float)(1 << depth);
         Box cube = {0, size, 0, size, 0, size};
-        float dist = box_entry(cube, origin, m.inv);
-        if (is_nan(dist) || dist < 0) return false;
-        m.t += dist + CCU_OFFSET;
+        float dist = box_entry(cube, origin, ms.inv);
+        if (is_nan(dist) || dist < 0) ms.entered = 0;
+        else ms.t += dist + CCU_OFFSET;
     }
-    return true;
+    return ms;
+}
+// returns false when the ray starts outside the octree cube and never enters it
+__device__ __forceinline__ bool march_begin(const DScene &s, March &m, float3 origin, float3 direction, float limit) {
+    const MarchStart ms = march_begin_core(s.depth, origin, direction);
+    m.o = origin;
+    m.d = direction;
+    m.inv = ms.inv;
+    m.t = ms.t;
+    m.limit = limit;
+    m.steps = 0;
+    return ms.entered != 0;
 }
 
 // The voxel the ray is in after marching m.t (octree.h:72-78): position, offset position and block coordinates.

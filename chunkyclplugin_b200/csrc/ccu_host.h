@@ -147,6 +147,7 @@ struct ccu_ctx {
     int q_bvh_warps = 23;
     int q_march_warps = 22;
     int window_spp = 0;
+    int closed_spp = 0;          // passes of the window closed by ccu_render_window_close, read-back in flight, not merged yet
     bool target_live = false;    // between ccu_render_begin and ccu_render_end
     ccu_render_params params = {256, 5, 13.0f, 0, 0};
     ccu_host::MergeJob merge;
@@ -160,6 +161,8 @@ struct ccu_ctx {
 
 namespace ccu_host {
 // internal entry points shared with ccu_group.cu (caller holds no lock)
+int start_readback(ccu_ctx *c, const float *src_dev, size_t lo, size_t hi, cudaStream_t stream);
+int merge_readback(ccu_ctx *c, size_t lo, size_t hi, double *sample_buffer, double ds, double dp, double sinv, unsigned max_threads);
 int merge_window_range(ccu_ctx *c, const float *src_dev, size_t lo, size_t hi, double *sample_buffer, double ds, double dp, double sinv,
                        cudaStream_t stream, unsigned max_threads);
 int replicate_scene(ccu_ctx *src, ccu_ctx *dst);

@@ -11,6 +11,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Tuning: CCU_NI_MATH keeps one out-of-line copy of the larger math helpers instead of inlining them at every use (the
+// wavefront kernel's shading stages are instruction-fetch bound; same arithmetic either way).
+#ifdef CCU_NI_MATH
+#define CCU_MATH_INLINE static __device__ __noinline__
+#else
+#define CCU_MATH_INLINE __device__ __forceinline__
+#endif
+
 namespace ccu {
 
 #define CCU_EPS 0.000005f    // constants.h:4
@@ -30,7 +38,7 @@ __device__ __forceinline__ float dot3(float3 a, float3 b) { return __fmaf_rn(a.z
 __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
     return f3(__fmaf_rn(a.y, b.z, -(a.z * b.y)), __fmaf_rn(a.z, b.x, -(a.x * b.z)), __fmaf_rn(a.x, b.y, -(a.y * b.x)));
 }
-__device__ __forceinline__ float3 normalize3(float3 v) {
+CCU_MATH_INLINE float3 normalize3(float3 v) {
     const float inf = __int_as_float(0x7f800000), qnan = __int_as_float(0x7fc00000);
     float ax = fabsf(v.x), ay = fabsf(v.y), az = fabsf(v.z);
     if (ax != ax || ay != ay || az != az) return f3(qnan, qnan, qnan);
@@ -51,7 +59,9 @@ __device__ __forceinline__ bool is_nan(float f) { return f != f; }
 __device__ __forceinline__ float nanf_() { return __int_as_float(0x7fc00000); }
 __device__ __forceinline__ float inff_() { return __int_as_float(0x7f800000); }
 
-__device__ __forceinline__ void dm_sincos(float x, float &s, float &c) {
+// (sin x, cos x) returned by value: an out-of-line copy then hands both back in registers
+CCU_MATH_INLINE float2 dm_sincos2(float x) {
+    float s, c;
     float kf = floorf(x * 0.636619772f + 0.5f);
     float r = x - kf * 1.5703125f;
     r = r - kf * 4.837512969970703125e-4f;
@@ -64,7 +74,9 @@ __device__ __forceinline__ void dm_sincos(float x, float &s, float &c) {
     float cc = (k & 1) ? sp : cp;
     s = (k & 2) ? -ss : ss;
     c = ((k + 1) & 2) ? -cc : cc;
+    return make_float2(s, c);
 }
+__device__ __forceinline__ void dm_sincos(float x, float &s, float &c) { const float2 r = dm_sincos2(x); s = r.x; c = r.y; }
 __device__ __forceinline__ float dm_cos(float x) { float s, c; dm_sincos(x, s, c); return c; }
 __device__ __forceinline__ float dm_sin(float x) { float s, c; dm_sincos(x, s, c); return s; }
 
@@ -77,7 +89,7 @@ __device__ __forceinline__ float dm_atan(float t) {
     float p = (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * t + t;
     return sign * (y0 + p);
 }
-__device__ __forceinline__ float dm_atan2(float y, float x) {
+CCU_MATH_INLINE float dm_atan2(float y, float x) {
     if (x != x || y != y) return nanf_();
     if (x > 0.0f) return dm_atan(y / x);
     if (x < 0.0f) return (y >= 0.0f) ? dm_atan(y / x) + 3.14159265358979f : dm_atan(y / x) - 3.14159265358979f;
@@ -85,7 +97,7 @@ __device__ __forceinline__ float dm_atan2(float y, float x) {
     if (y < 0.0f) return -1.5707963267948966f;
     return 0.0f;
 }
-__device__ __forceinline__ float dm_asin(float x) {
+CCU_MATH_INLINE float dm_asin(float x) {
     float a = fabsf(x);
     if (a > 1.0f) return nanf_();
     bool big = a > 0.5f;

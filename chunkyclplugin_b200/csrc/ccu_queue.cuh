@@ -76,6 +76,7 @@ constexpr int Q_TOP_WORDS = 4096;            // top tables up to 16^3 cells are 
 #ifndef CCU_Q_STACK
 #define CCU_Q_STACK 20
 #endif
+constexpr int Q_SMEM_LIMIT = 227 * 1024 - 1280;   // dynamic shared memory a CTA may ask for, less the kernel's static tables (SmemTables)
 constexpr int Q_STACK = CCU_Q_STACK;
 constexpr int Q_STACK_WORDS = Q_STACK * Q_WARPS * 32;
 __host__ __device__ constexpr int q_fields(bool bvh) { return bvh ? (int)QF_COUNT_BVH : (int)QF_COUNT; }
@@ -114,6 +115,7 @@ struct QueueParams {
     int bvh_warps;     // scheduler: only warps 0 .. bvh_warps-1 run the BVH stage
     int march_warps;   // scheduler: only warps 0 .. march_warps-1 run the MARCH stage
     int march_bias;    // scheduler: warps of sub-partitions 0..2 count MARCH columns +bias, warps of sub-partition 3 -bias
+    int sky_texels;    // > 0: the launch reserved this many texels (4 bytes each) behind the other shared arrays for the sky table
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -667,6 +669,13 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
         const int n = 1 << (3 * s.air_top_log2);
         for (int i = threadIdx.x; i < n; i += blockDim.x) top_s[i] = __ldg(s.air_top + i);
     }
+    // sky / UNORM tables (sky.h:95-106 reads four texels per lookup)
+    uchar4 *sky_s = nullptr;
+    if (qp.sky_texels > 0) {
+        sky_s = reinterpret_cast<uchar4 *>(top_s + (LAY == 0 ? Q_TOP_WORDS : 0) + (HAS_BVH ? Q_STACK_WORDS : 0));
+        for (int i = threadIdx.x; i < qp.sky_texels; i += blockDim.x) sky_s[i] = __ldg(s.sky + i);
+    }
+    stage_tables(s, sky_s);
     if (threadIdx.x == 0) {
         live[0] = Q_SLOTS;
         live[1] = 0;                 // tile lock

@@ -48,6 +48,7 @@ __global__ void k_sun_setup(const int *sun_words, float *out /* su sv sw radius_
 template <int MODE>
 __global__ void __launch_bounds__(128) k_render_mega(const __grid_constant__ DScene s, const int *__restrict__ seeds, int n_passes,
                                                      int start_spp, float *res, const float *res_prev, int n_pixels) {
+    stage_tables(s, nullptr);
     for (int gid = blockIdx.x * blockDim.x + threadIdx.x; gid < n_pixels; gid += gridDim.x * blockDim.x) {
         float *px = res + (size_t)gid * 3;
         const float *pp = res_prev + (size_t)gid * 3;    // what the reference's single buffer holds when the window starts
@@ -82,6 +83,7 @@ __device__ __forceinline__ int face_of(float3 n) {
 template <int MODE>
 __global__ void __launch_bounds__(256) k_first_hit(const __grid_constant__ DScene s, int seed, int n_pixels, int *block, int *face, int *node,
                                                    int *kind, float *t, float *normal, float *color) {
+    stage_tables(s, nullptr);
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= (unsigned)n_pixels) return;
     const int gid = tile_order_pixel(k, s.width, s.height);
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(256) k_first_hit(const __grid_constant__ DScen
 // rayTracer.cl:141-216
 template <int MODE>
 __global__ void __launch_bounds__(256) k_preview(const __grid_constant__ DScene s, int n_pixels, int *res) {
+    stage_tables(s, nullptr);
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= (unsigned)n_pixels) return;
     const int gid = tile_order_pixel(k, s.width, s.height);
@@ -377,31 +380,41 @@ cudaError_t allow_smem(K kernel, int bytes) { return cudaFuncSetAttribute(kernel
 
 namespace ccu_host {
 
-// Read floats [lo, hi) of `src_dev` (a finished window's running mean) back through the pinned staging buffer in chunks on
-// `st` and fold each chunk into the host sample buffer as it lands (OpenClPathTracingRenderer.java:164-173):
-//   sample[i] = (sample[i] * ds + mean[i] * dp) * sinv
-int merge_window_range(ccu_ctx *c, const float *src_dev, size_t lo, size_t hi, double *sample_buffer, double ds, double dp, double sinv,
-                       cudaStream_t st, unsigned max_threads) {
-    if (hi <= lo) return CCU_OK;
-    constexpr int NCH = 8;
-    const size_t n = hi - lo;
-    const size_t chunk = ((n + NCH - 1) / NCH + 63) & ~(size_t)63;
-    for (int k = 0; k < NCH; k++) {
+// Read-back of a finished window, in two phases so that the copy overlaps whatever the host does in between:
+// start_readback queues the copy of floats [lo, hi) of `src_dev` (indexed by absolute float offset) into the pinned staging
+// buffer in chunks on `st`, one event per chunk; merge_readback waits chunk by chunk and folds each into the host sample buffer
+// (OpenClPathTracingRenderer.java:164-173):  sample[i] = (sample[i] * ds + mean[i] * dp) * sinv
+constexpr int MERGE_CHUNKS = 8;
+static size_t merge_chunk_len(size_t n) { return ((n + MERGE_CHUNKS - 1) / MERGE_CHUNKS + 63) & ~(size_t)63; }
+
+int start_readback(ccu_ctx *c, const float *src_dev, size_t lo, size_t hi, cudaStream_t st) {
+    const size_t n = hi > lo ? hi - lo : 0;
+    const size_t chunk = merge_chunk_len(n);
+    for (int k = 0; k < MERGE_CHUNKS; k++) {
         const size_t a = lo + std::min(n, k * chunk), b = lo + std::min(n, (k + 1) * chunk);
         if (b > a) CU(cudaMemcpyAsync(c->pinned + a, src_dev + a, (b - a) * sizeof(float), cudaMemcpyDeviceToHost, st));
         CU(cudaEventRecord(c->chunk_ev[k], st));
     }
+    return CCU_OK;
+}
+
+int merge_readback(ccu_ctx *c, size_t lo, size_t hi, double *sample_buffer, double ds, double dp, double sinv, unsigned max_threads) {
+    if (hi <= lo) return CCU_OK;
+    const size_t n = hi - lo;
+    const size_t chunk = merge_chunk_len(n);
     unsigned hw = std::thread::hardware_concurrency();
     unsigned nt = std::max(1u, std::min(std::min(16u, max_threads), hw ? hw : 4u));
     if (n < (1u << 20)) nt = 1;
     const float *src = c->pinned;
     cudaEvent_t *evs = c->chunk_ev;
     const int device = c->device;
-    auto work = [=](unsigned t) {
+    std::vector<cudaError_t> errs(nt, cudaSuccess);
+    auto work = [&, device](unsigned t) {
         cudaSetDevice(device);
-        for (int k = 0; k < NCH; k++) {
+        for (int k = 0; k < MERGE_CHUNKS; k++) {
             const size_t a = lo + std::min(n, k * chunk), b = lo + std::min(n, (k + 1) * chunk);
-            cudaEventSynchronize(evs[k]);
+            const cudaError_t e = cudaEventSynchronize(evs[k]);
+            if (e != cudaSuccess) { errs[t] = e; return; }
             const size_t len = b - a, part = (len + nt - 1) / nt;
             const size_t i0 = a + std::min(len, t * part), i1 = a + std::min(len, (t + 1) * part);
             for (size_t i = i0; i < i1; i++) sample_buffer[i] = (sample_buffer[i] * ds + (double)src[i] * dp) * sinv;
@@ -414,8 +427,16 @@ int merge_window_range(ccu_ctx *c, const float *src_dev, size_t lo, size_t hi, d
         for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
         for (auto &t : th) t.join();
     }
-    CU(cudaStreamSynchronize(st));
+    for (cudaError_t e : errs)
+        if (e != cudaSuccess) return fail(CCU_ECUDA, "window read-back: %s", cudaGetErrorString(e));
     return CCU_OK;
+}
+
+int merge_window_range(ccu_ctx *c, const float *src_dev, size_t lo, size_t hi, double *sample_buffer, double ds, double dp, double sinv,
+                       cudaStream_t st, unsigned max_threads) {
+    int rc = start_readback(c, src_dev, lo, hi, st);
+    if (rc != CCU_OK) return rc;
+    return merge_readback(c, lo, hi, sample_buffer, ds, dp, sinv, max_threads);
 }
 
 template <class T>
@@ -523,12 +544,12 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->window_ev, cudaEventDisableTiming);
     for (int k = 0; k < 8 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming);
     for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&c->rays_used[k], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = allow_smem(k_render_queue<false, 0>, q_smem_bytes(false, true));
-    if (e == cudaSuccess) e = allow_smem(k_render_queue<false, 1>, q_smem_bytes(false, false));
-    if (e == cudaSuccess) e = allow_smem(k_render_queue<false, 2>, q_smem_bytes(false, false));
-    if (e == cudaSuccess) e = allow_smem(k_render_queue<true, 0>, q_smem_bytes(true, true));
-    if (e == cudaSuccess) e = allow_smem(k_render_queue<true, 1>, q_smem_bytes(true, false));
-    if (e == cudaSuccess) e = allow_smem(k_render_queue<true, 2>, q_smem_bytes(true, false));
+    if (e == cudaSuccess) e = allow_smem(k_render_queue<false, 0>, Q_SMEM_LIMIT);
+    if (e == cudaSuccess) e = allow_smem(k_render_queue<false, 1>, Q_SMEM_LIMIT);
+    if (e == cudaSuccess) e = allow_smem(k_render_queue<false, 2>, Q_SMEM_LIMIT);
+    if (e == cudaSuccess) e = allow_smem(k_render_queue<true, 0>, Q_SMEM_LIMIT);
+    if (e == cudaSuccess) e = allow_smem(k_render_queue<true, 1>, Q_SMEM_LIMIT);
+    if (e == cudaSuccess) e = allow_smem(k_render_queue<true, 2>, Q_SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaMalloc(&c->unorm, 256 * sizeof(float));
     if (e == cudaSuccess) {
         k_unorm_table<<<1, 256, 0, c->stream>>>(c->unorm);
@@ -821,6 +842,7 @@ int ccu_render_end(ccu_ctx *c) {
     // the buffers stay cached for the next render of the same size (freed by ccu_ctx_destroy / a size change)
     c->target_live = false;
     c->window_spp = 0;
+    c->closed_spp = 0;
     return rc != CCU_OK ? rc : rc2;
 }
 
@@ -852,6 +874,7 @@ int ccu_render_begin(ccu_ctx *c, int32_t width, int32_t height) {
     c->width = width;
     c->height = height;
     c->window_spp = 0;
+    c->closed_spp = 0;
     c->target_live = true;
     return CCU_OK;
 }
@@ -928,7 +951,12 @@ static int render_passes_locked(ccu_ctx *c, const int32_t *seeds, int32_t n_pass
         qp.march_warps = bvh ? 64 : c->q_march_warps;   // with BVHs the service warps are the ones that do not walk
         const int lay = air_layout_id(c);
         const int grid = c->sm_count, block = Q_WARPS * 32;
-        const int smem = q_smem_bytes(bvh, lay == 0);
+        // the sky table is staged in shared memory when it fits beside the path pool (128 x 128 texels = 64 KiB)
+        const int sky_texels = c->sky_res * c->sky_res;
+        const int base_smem = q_smem_bytes(bvh, lay == 0);
+        const bool sky_smem = getenv("CCU_NO_SKY_SMEM") == nullptr && sky_texels <= 16384 && base_smem + sky_texels * 4 <= Q_SMEM_LIMIT;
+        qp.sky_texels = sky_smem ? sky_texels : 0;
+        const int smem = base_smem + qp.sky_texels * 4;
         if (bvh) {
             if (lay == 0) k_render_queue<true, 0><<<grid, block, smem, c->stream>>>(c->scene, qp);
             else if (lay == 1) k_render_queue<true, 1><<<grid, block, smem, c->stream>>>(c->scene, qp);
@@ -1008,6 +1036,7 @@ int ccu_render_read(ccu_ctx *c, float *mean_rgb, int32_t *window_spp) {
     if (!c->accum[0] || !c->target_live) return fail(CCU_ESTATE, "ccu_render_read: no render target");
     rc = join_merge_locked(c, lk);
     if (rc != CCU_OK) return rc;
+    if (c->closed_spp > 0) return fail(CCU_ESTATE, "ccu_render_read: a closed window is waiting for ccu_render_window_merge (it owns the staging buffer)");
     DeviceGuard g(c->device);
     const size_t n = (size_t)c->width * c->height * 3;
     CU(cudaMemcpyAsync(c->pinned, c->accum[c->accum_active], n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1024,44 +1053,80 @@ int ccu_render_merge_wait(ccu_ctx *c) {
     return join_merge_locked(c, lk);
 }
 
-int ccu_render_merge_async(ccu_ctx *c, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp) {
-    if (!c || !sample_buffer) return fail(CCU_EINVAL, "ccu_render_merge: null argument");
-    if (sample_spp < 0) return fail(CCU_EINVAL, "ccu_render_merge: negative spp");
-    std::unique_lock<std::mutex> lk(c->mu);
-    if (!c->accum[0] || !c->target_live) return fail(CCU_ESTATE, "ccu_render_merge: no render target");
-    int rc = join_merge_locked(c, lk);       // one merge at a time: they share the staging buffer and the sample buffer
+// closes the window under the lock: the passes that follow accumulate in the other buffer (the first of them still reads
+// what this buffer holds, like the reference's single buffer at bufferSpp = 0, rayTracer.cl:111); the read-back starts
+static int window_close_locked(ccu_ctx *c, std::unique_lock<std::mutex> &lk, int32_t *window_spp) {
+    if (!c->accum[0] || !c->target_live) return fail(CCU_ESTATE, "no render target");
+    int rc = join_merge_locked(c, lk);       // one merge at a time: they share the staging buffer
     if (rc != CCU_OK) return rc;
+    if (c->closed_spp > 0) return fail(CCU_ESTATE, "the previous window was closed but not merged (ccu_render_window_merge)");
     const int pass_spp = c->window_spp;
-    if (merged_spp) *merged_spp = pass_spp;
+    if (window_spp) *window_spp = pass_spp;
     if (pass_spp == 0) return CCU_OK;
     DeviceGuard g(c->device);
-    // close the window: the passes that follow accumulate in the other buffer (the first of them still reads what this
-    // buffer holds, like the reference's single buffer at bufferSpp = 0, rayTracer.cl:111)
     CU(cudaEventRecord(c->window_ev, c->stream));
     const float *src = c->accum[c->accum_active];
     c->accum_active ^= 1;
     c->window_base = src;
     c->window_spp = 0;   // bufferSppReal = 0 (:170)
+    c->closed_spp = pass_spp;
+    CU(cudaStreamWaitEvent(c->copy_stream, c->window_ev, 0));
+    return ccu_host::start_readback(c, src, 0, (size_t)c->width * c->height * 3, c->copy_stream);
+}
+
+int ccu_render_window_close(ccu_ctx *c, int32_t *window_spp) {
+    if (!c) return fail(CCU_EINVAL, "ccu_render_window_close: null context");
+    std::unique_lock<std::mutex> lk(c->mu);
+    return window_close_locked(c, lk, window_spp);
+}
+
+int ccu_render_window_merge(ccu_ctx *c, double *sample_buffer, int32_t sample_spp) {
+    if (!c || !sample_buffer) return fail(CCU_EINVAL, "ccu_render_window_merge: null argument");
+    if (sample_spp < 0) return fail(CCU_EINVAL, "ccu_render_window_merge: negative spp");
+    int pass_spp;
+    size_t n;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        pass_spp = c->closed_spp;
+        n = (size_t)c->width * c->height * 3;
+    }
+    if (pass_spp == 0) return CCU_OK;
     const double sinv = 1.0 / (double)(sample_spp + pass_spp);
-    const double ds = (double)sample_spp, dp = (double)pass_spp;
-    const size_t n = (size_t)c->width * c->height * 3;
+    // the wait for the copies and the merge itself run outside the context lock: the next window renders meanwhile
+    int rc = ccu_host::merge_readback(c, 0, n, sample_buffer, (double)sample_spp, (double)pass_spp, sinv, 16);
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->closed_spp = 0;
+    return rc;
+}
+
+int ccu_render_merge_async(ccu_ctx *c, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp) {
+    if (!c || !sample_buffer) return fail(CCU_EINVAL, "ccu_render_merge: null argument");
+    if (sample_spp < 0) return fail(CCU_EINVAL, "ccu_render_merge: negative spp");
+    std::unique_lock<std::mutex> lk(c->mu);
+    int32_t pass_spp = 0;
+    int rc = window_close_locked(c, lk, &pass_spp);
+    if (merged_spp) *merged_spp = pass_spp;
+    if (rc != CCU_OK || pass_spp == 0) return rc;
     c->merge.active = true;
     c->merge.status = CCU_OK;
     c->merge.worker = std::thread([=] {
-        cudaSetDevice(c->device);
-        int st = CCU_OK;
-        cudaError_t e = cudaStreamWaitEvent(c->copy_stream, c->window_ev, 0);
-        if (e != cudaSuccess) st = fail(CCU_ECUDA, "merge: %s", cudaGetErrorString(e));
-        if (st == CCU_OK) st = ccu_host::merge_window_range(c, src, 0, n, sample_buffer, ds, dp, sinv, c->copy_stream, 16);
+        const int st = ccu_render_window_merge(c, sample_buffer, sample_spp);
         if (st != CCU_OK) { c->merge.status = st; c->merge.error = ccu_host::last_error(); }
     });
     return CCU_OK;
 }
 
 int ccu_render_merge(ccu_ctx *c, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp) {
-    int rc = ccu_render_merge_async(c, sample_buffer, sample_spp, merged_spp);
-    if (rc != CCU_OK) return rc;
-    rc = ccu_render_merge_wait(c);
+    if (!c || !sample_buffer) return fail(CCU_EINVAL, "ccu_render_merge: null argument");
+    if (sample_spp < 0) return fail(CCU_EINVAL, "ccu_render_merge: negative spp");
+    int32_t pass_spp = 0;
+    {
+        std::unique_lock<std::mutex> lk(c->mu);
+        int rc = window_close_locked(c, lk, &pass_spp);
+        if (merged_spp) *merged_spp = pass_spp;
+        if (rc != CCU_OK) return rc;
+    }
+    int rc = ccu_render_window_merge(c, sample_buffer, sample_spp);
     if (rc != CCU_OK) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);

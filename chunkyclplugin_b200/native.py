@@ -67,6 +67,8 @@ SYMBOLS = {
     "ccu_render_merge": (C.c_int, [_vp, _vp, _i32, _pi32]),
     "ccu_render_merge_async": (C.c_int, [_vp, _vp, _i32, _pi32]),
     "ccu_render_merge_wait": (C.c_int, [_vp]),
+    "ccu_render_window_close": (C.c_int, [_vp, _pi32]),
+    "ccu_render_window_merge": (C.c_int, [_vp, _vp, _i32]),
     "ccu_render_reset_window": (C.c_int, [_vp]),
     "ccu_render_set_window_spp": (C.c_int, [_vp, _i32]),
     "ccu_render_end": (C.c_int, [_vp]),
@@ -276,6 +278,16 @@ class Context:
     def render_merge_wait(self):
         check(self._lib.ccu_render_merge_wait(self._h))
         self._merge_keepalive = None
+
+    def render_window_close(self) -> int:
+        """Closes the window and starts its read-back; returns the window's passes (merge it with render_window_merge)."""
+        m = C.c_int32()
+        check(self._lib.ccu_render_window_close(self._h, C.byref(m)))
+        return m.value
+
+    def render_window_merge(self, sample_buffer: np.ndarray, sample_spp: int):
+        assert sample_buffer.dtype == np.float64 and sample_buffer.flags.c_contiguous
+        check(self._lib.ccu_render_window_merge(self._h, _ptr(sample_buffer), sample_spp))
 
     def render_reset_window(self):
         check(self._lib.ccu_render_reset_window(self._h))

@@ -108,6 +108,12 @@ int ccu_render_merge(ccu_ctx *ctx, double *sample_buffer, int32_t sample_spp, in
  * merge / ccu_render_end, which wait implicitly).  *merged_spp = passes of the closed window. */
 int ccu_render_merge_async(ccu_ctx *ctx, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp);
 int ccu_render_merge_wait(ccu_ctx *ctx);   /* bufferMergeTask.join() */
+/* The same in two calls, for hosts that run the merge on a thread of their own (the Java shim: Chunky.getCommonThreads(), with the
+ * heap array passed as a critical segment): ccu_render_window_close closes the window and starts the read-back (returns at once;
+ * call it on the render thread before the next ccu_render_passes); ccu_render_window_merge - any thread - waits for the copies
+ * and merges.  Exactly one merge per close. */
+int ccu_render_window_close(ccu_ctx *ctx, int32_t *window_spp);
+int ccu_render_window_merge(ccu_ctx *ctx, double *sample_buffer, int32_t sample_spp);
 int ccu_render_reset_window(ccu_ctx *ctx); /* bufferSppReal = 0 (:170); the buffer itself is not cleared, as in the reference */
 /* multi-GPU: after the window buffers of all ranks have been reduced into this context's buffer (mean over all passes), tell it how
  * many passes the buffer now stands for, so that ccu_render_merge / ccu_render_read weight it correctly (bufferSppReal of :167-173) */

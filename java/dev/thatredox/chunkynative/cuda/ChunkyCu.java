@@ -6,7 +6,7 @@ import java.lang.invoke.MethodHandle;
 import static java.lang.foreign.ValueLayout.*;
 
 /**
- * Java FFM (JDK 22+, java.lang.foreign) binding of libchunkycu.so - include/chunkycu.h.
+ * Java FFM (JDK 22+, java.lang.foreign; critical downcalls with heap segments need 22) binding of libchunkycu.so - include/chunkycu.h.
  *
  * Drop-in replacement for the JOCL calls of the reference plugin; one method per C entry point.  A JNI variant
  * is a mechanical translation (see INTEGRATION.md).  NOT COMPILED in the build image (no JDK there).
@@ -46,12 +46,39 @@ public final class ChunkyCu {
     private static final MethodHandle SCENE_COMMIT = h("ccu_scene_commit", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle CAMERA_SET = h("ccu_camera_set", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG));
     private static final MethodHandle RENDER_BEGIN = h("ccu_render_begin", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
+    private static final MethodHandle RENDER_SET_PARAMS = h("ccu_render_set_params", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle RENDER_PASSES = h("ccu_render_passes", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+    private static final MethodHandle RENDER_PASSES_ASYNC = h("ccu_render_passes_async", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+    private static final MethodHandle RENDER_SYNC = h("ccu_render_sync", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle WINDOW_CLOSE = h("ccu_render_window_close", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    // the merge reads and writes Chunky's double[] in place: a critical downcall may take the heap array itself (no 50 MB copy)
+    private static final MethodHandle WINDOW_MERGE = LINKER.downcallHandle(LIB.find("ccu_render_window_merge").orElseThrow(() -> new UnsatisfiedLinkError("ccu_render_window_merge")),
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT), Linker.Option.critical(true));
+    private static final MethodHandle LAST_KERNEL_MS = h("ccu_last_kernel_ms", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle RENDER_READ = h("ccu_render_read", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
-    private static final MethodHandle RENDER_MERGE = h("ccu_render_merge", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
+    private static final MethodHandle RENDER_MERGE = LINKER.downcallHandle(LIB.find("ccu_render_merge").orElseThrow(() -> new UnsatisfiedLinkError("ccu_render_merge")),
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS), Linker.Option.critical(true));
     private static final MethodHandle RENDER_END = h("ccu_render_end", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle PREVIEW = h("ccu_preview", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle TONEMAP = h("ccu_tonemap", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_FLOAT, ADDRESS, JAVA_INT, ADDRESS));
+    // multi-GPU group (include/chunkycu.h "multi-GPU"): one JVM drives all GPUs of the box
+    private static final MethodHandle GROUP_CREATE = h("ccu_group_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    private static final MethodHandle GROUP_DESTROY = h("ccu_group_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle GROUP_MEMBER = h("ccu_group_member", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    private static final MethodHandle GROUP_REPLICATE = h("ccu_group_replicate_scene", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle GROUP_CAMERA_SET = h("ccu_group_camera_set", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG));
+    private static final MethodHandle GROUP_RENDER_BEGIN = h("ccu_group_render_begin", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
+    private static final MethodHandle GROUP_RENDER_SET_PARAMS = h("ccu_group_render_set_params", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle GROUP_RENDER_PASSES = h("ccu_group_render_passes", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+    private static final MethodHandle GROUP_RENDER_SYNC = h("ccu_group_render_sync", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle GROUP_RENDER_MERGE = LINKER.downcallHandle(LIB.find("ccu_group_render_merge").orElseThrow(() -> new UnsatisfiedLinkError("ccu_group_render_merge")),
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS), Linker.Option.critical(true));
+    private static final MethodHandle GROUP_RENDER_END = h("ccu_group_render_end", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+
+    /** ccu_render_params.flags: Chunky's "draw entities" / sunlight toggles as launch parameters (reference README.md:31-35). */
+    public static final int RENDER_NO_ENTITIES = 1, RENDER_NO_SUN = 2;
+    private static final StructLayout RENDER_PARAMS = MemoryLayout.structLayout(JAVA_INT.withName("draw_depth"), JAVA_INT.withName("max_depth"),
+            JAVA_FLOAT.withName("emitter_scale"), JAVA_INT.withName("kernel"), JAVA_INT.withName("flags"));
 
     private ChunkyCu() {}
 
@@ -70,8 +97,13 @@ public final class ChunkyCu {
     /** One ccu_ctx; AutoCloseable like the reference's ClMemory handles (ClMemory.java:12-29). */
     public static final class Context implements AutoCloseable {
         private MemorySegment handle;
+        private final boolean owned;
+
+        /** A member context of a {@link Group}: borrowed, closed with the group. */
+        Context(MemorySegment borrowed) { handle = borrowed; owned = false; }
 
         public Context(int deviceIndex) {
+            owned = true;
             try (Arena a = Arena.ofConfined()) {
                 MemorySegment out = a.allocate(ADDRESS);
                 check((int) CTX_CREATE.invokeExact(deviceIndex, out));
@@ -136,20 +168,53 @@ public final class ChunkyCu {
             }
         }
         public void renderBegin(int width, int height) { check(call(RENDER_BEGIN, handle, width, height)); }
+        /** drawDepth (scene ray depth UI), maxDepth, emitter scale, kernel (0 = auto) and the RENDER_* toggles. */
+        public void renderSetParams(int drawDepth, int maxDepth, float emitterScale, int kernel, int flags) {
+            try (Arena a = Arena.ofConfined()) {
+                MemorySegment p = a.allocate(RENDER_PARAMS);
+                p.set(JAVA_INT, 0, drawDepth); p.set(JAVA_INT, 4, maxDepth); p.set(JAVA_FLOAT, 8, emitterScale);
+                p.set(JAVA_INT, 12, kernel); p.set(JAVA_INT, 16, flags);
+                check(call(RENDER_SET_PARAMS, handle, p));
+            }
+        }
         public void renderPasses(int[] seeds) {
             try (Arena a = Arena.ofConfined()) {
                 check(call(RENDER_PASSES, handle, a.allocateFrom(JAVA_INT, seeds), seeds.length));
             }
         }
-        /** Fused read + weighted merge into Chunky's sample buffer (OpenClPathTracingRenderer.java:164-173). */
+        /** Returns after the enqueue; renderSync() waits (without holding the context lock, so previews / tonemaps go through). */
+        public void renderPassesAsync(int[] seeds) {
+            try (Arena a = Arena.ofConfined()) {
+                check(call(RENDER_PASSES_ASYNC, handle, a.allocateFrom(JAVA_INT, seeds), seeds.length));
+            }
+        }
+        public void renderSync() { check(call(RENDER_SYNC, handle)); }
+        public float lastKernelMs() {
+            try (Arena a = Arena.ofConfined()) {
+                MemorySegment ms = a.allocate(JAVA_FLOAT);
+                check(call(LAST_KERNEL_MS, handle, ms));
+                return ms.get(JAVA_FLOAT, 0);
+            }
+        }
+        /** Fused read + weighted merge into Chunky's sample buffer (OpenClPathTracingRenderer.java:164-173); blocking. */
         public int renderMerge(double[] sampleBuffer, int sampleSpp) {
             try (Arena a = Arena.ofConfined()) {
-                MemorySegment buf = a.allocateFrom(JAVA_DOUBLE, sampleBuffer);
                 MemorySegment merged = a.allocate(JAVA_INT);
-                check(call(RENDER_MERGE, handle, buf, sampleSpp, merged));
-                MemorySegment.copy(buf, JAVA_DOUBLE, 0, sampleBuffer, 0, sampleBuffer.length);
+                check(call(RENDER_MERGE, handle, MemorySegment.ofArray(sampleBuffer), sampleSpp, merged));
                 return merged.get(JAVA_INT, 0);
             }
+        }
+        /** Closes the window (the next passes go to the second buffer) and starts its read-back; returns its pass count. */
+        public int windowClose() {
+            try (Arena a = Arena.ofConfined()) {
+                MemorySegment n = a.allocate(JAVA_INT);
+                check(call(WINDOW_CLOSE, handle, n));
+                return n.get(JAVA_INT, 0);
+            }
+        }
+        /** The merge of the closed window; runs on a Chunky common-pool thread while the render thread queues the next passes. */
+        public void windowMerge(double[] sampleBuffer, int sampleSpp) {
+            check(call(WINDOW_MERGE, handle, MemorySegment.ofArray(sampleBuffer), sampleSpp));
         }
         public void renderEnd() { check(call(RENDER_END, handle)); }
         public void preview(int[] argb) {
@@ -173,9 +238,61 @@ public final class ChunkyCu {
         @Override
         public void close() {
             if (handle != null) {
-                call(CTX_DESTROY, handle);
+                if (owned) call(CTX_DESTROY, handle);
                 handle = null;
             }
+        }
+    }
+
+    /** N GPUs rendering one image (ccu_group_*): scene uploaded to member 0 and replicated over NVLink, passes striped, one
+     *  NCCL reduce-scatter per window, every GPU merging its share of the sample buffer. */
+    public static final class Group implements AutoCloseable {
+        private MemorySegment handle;
+        public final int size;
+
+        public Group(int[] devices) {
+            try (Arena a = Arena.ofConfined()) {
+                MemorySegment out = a.allocate(ADDRESS);
+                check((int) GROUP_CREATE.invokeExact(a.allocateFrom(JAVA_INT, devices), devices.length, out));
+                handle = out.get(ADDRESS, 0);
+                size = devices.length;
+            } catch (RuntimeException e) {
+                throw e;
+            } catch (Throwable t) {
+                throw new RuntimeException(t);
+            }
+        }
+        /** Member 0 is the context the scene loader uploads to. */
+        public Context member(int i) {
+            try (Arena a = Arena.ofConfined()) {
+                MemorySegment out = a.allocate(ADDRESS);
+                check(Context.call(GROUP_MEMBER, handle, i, out));
+                return new Context(out.get(ADDRESS, 0));
+            }
+        }
+        public void replicateScene() { check(Context.call(GROUP_REPLICATE, handle)); }
+        public void cameraSet(int projectorType, float[] settings) {
+            try (Arena a = Arena.ofConfined()) {
+                check(Context.call(GROUP_CAMERA_SET, handle, projectorType, a.allocateFrom(JAVA_FLOAT, settings), (long) settings.length));
+            }
+        }
+        public void renderBegin(int width, int height) { check(Context.call(GROUP_RENDER_BEGIN, handle, width, height)); }
+        public void renderPasses(int[] seeds) {
+            try (Arena a = Arena.ofConfined()) {
+                check(Context.call(GROUP_RENDER_PASSES, handle, a.allocateFrom(JAVA_INT, seeds), seeds.length));
+            }
+        }
+        public void renderSync() { check(Context.call(GROUP_RENDER_SYNC, handle)); }
+        public int renderMerge(double[] sampleBuffer, int sampleSpp) {
+            try (Arena a = Arena.ofConfined()) {
+                MemorySegment merged = a.allocate(JAVA_INT);
+                check(Context.call(GROUP_RENDER_MERGE, handle, MemorySegment.ofArray(sampleBuffer), sampleSpp, merged));
+                return merged.get(JAVA_INT, 0);
+            }
+        }
+        public void renderEnd() { check(Context.call(GROUP_RENDER_END, handle)); }
+        @Override public void close() {
+            if (handle != null) { Context.call(GROUP_DESTROY, handle); handle = null; }
         }
     }
 

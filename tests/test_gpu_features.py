@@ -217,6 +217,32 @@ def test_async_merge_racing_the_next_window_is_bit_identical(scenes, cuda_ctx):
     assert got.max() > 0
 
 
+def test_window_close_then_merge_on_another_thread(scenes, cuda_ctx):
+    """The two-call form the Java shim uses: close on the render thread, merge on a pool thread while the next window renders."""
+    from chunkyclplugin_b200 import native
+    p = scenes("terrain256")
+    seeds = pass_seeds(12)
+    n = p.width * p.height * 3
+    load_scene(cuda_ctx, p)
+    want = np.zeros(n, np.float64)
+    cuda_ctx.render_passes(seeds[:6]); cuda_ctx.render_merge(want, 0)
+    cuda_ctx.render_passes(seeds[6:]); cuda_ctx.render_merge(want, 6)
+    load_scene(cuda_ctx, p)
+    got = np.zeros(n, np.float64)
+    cuda_ctx.render_passes(seeds[:6])
+    assert cuda_ctx.render_window_close() == 6
+    with pytest.raises(native.ChunkyCuError):
+        cuda_ctx.render_read()                                     # the closed window owns the staging buffer
+    t = threading.Thread(target=cuda_ctx.render_window_merge, args=(got, 0))
+    t.start()
+    cuda_ctx.render_passes(seeds[6:])                              # renders into the second buffer meanwhile
+    t.join()
+    assert cuda_ctx.render_window_close() == 6
+    cuda_ctx.render_window_merge(got, 6)
+    assert cuda_ctx.render_window_close() == 0                     # nothing open: nothing to merge
+    assert np.array_equal(got, want)
+
+
 def test_window_start_reads_the_previous_windows_mean(scenes, cuda_ctx):
     """With two window buffers the first pass of a window still sees what the reference's single buffer would hold
     (mean * 0 + colour, rayTracer.cl:111): an inf left by the previous window turns into NaN there, and here."""
