@@ -35,9 +35,13 @@ NcclApi *nccl() {
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
-        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        // CCU_NCCL_LIB names the copy to use; a process that will also load another NCCL user (a Python host with torch)
+        // must end up with ONE libnccl.so.2 that is new enough for both - the loader shares by soname whichever came first
+        // (chunkyclplugin_b200/native.py points CCU_NCCL_LIB at the NCCL bundled with torch when there is one).
+        const char *names[] = {getenv("CCU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
         for (const char *n : names) {
-            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (!n || !*n) continue;
+            api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
             if (api.lib) break;
         }
         if (!api.lib) { api.why = std::string("libnccl.so.2 not loadable: ") + dlerror(); return; }
@@ -85,6 +89,12 @@ struct ccu_group {
     int reduced_total = 0;              // passes of the window whose sum sits in the share buffers (reduced, not yet merged)
     bool reduced_equal = true;          // ... and whether that sum is a sum of means (equal pass counts) or of window sums
     float render_ms = 0, reduce_ms = 0;
+    // asynchronous share merge (ccu_group_render_merge_async): the reduce-scatter result sits in the share buffers, so the next
+    // window may render while the shares travel to the host and are merged
+    std::thread merge_worker;
+    bool merge_active = false;
+    int merge_status = CCU_OK;
+    std::string merge_error;
 };
 
 namespace {
@@ -211,6 +221,7 @@ int ccu_group_join(ccu_ctx *ctx, const uint8_t id[CCU_UNIQUE_ID_BYTES], int32_t 
 
 int ccu_group_destroy(ccu_group *g) {
     if (!g) return CCU_OK;
+    ccu_group_render_merge_wait(g);
     for (auto &m : g->local) free_member(m);
     delete g;
     return CCU_OK;
@@ -322,6 +333,8 @@ int ccu_group_render_sync(ccu_group *g) {
     return CCU_OK;
 }
 
+static int join_group_merge(ccu_group *g, std::unique_lock<std::mutex> &lk);
+
 // window means -> (sum over GPUs) in the share buffers; closes the window.  Caller holds g->mu.
 static int reduce_window_locked(ccu_group *g) {
     const int total = g->window_total;
@@ -384,19 +397,43 @@ static int finish_reduce_timing(ccu_group *g) {
 
 int ccu_group_render_reduce(ccu_group *g, int32_t *window_spp) {
     if (!g) return fail(CCU_EINVAL, "ccu_group_render_reduce: null group");
-    std::lock_guard<std::mutex> lk(g->mu);
+    std::unique_lock<std::mutex> lk(g->mu);
     if (window_spp) *window_spp = g->window_total;
-    int rc = reduce_window_locked(g);
+    int rc = join_group_merge(g, lk);
+    if (rc != CCU_OK) return rc;
+    rc = reduce_window_locked(g);
     if (rc != CCU_OK) return rc;
     return finish_reduce_timing(g);
 }
 
-int ccu_group_render_merge(ccu_group *g, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp) {
-    if (!g || !sample_buffer) return fail(CCU_EINVAL, "ccu_group_render_merge: null argument");
-    if (sample_spp < 0) return fail(CCU_EINVAL, "ccu_group_render_merge: negative spp");
-    std::lock_guard<std::mutex> lk(g->mu);
+static int join_group_merge(ccu_group *g, std::unique_lock<std::mutex> &lk) {
+    if (!g->merge_active) return CCU_OK;
+    std::thread t = std::move(g->merge_worker);
+    lk.unlock();
+    if (t.joinable()) t.join();
+    lk.lock();
+    g->merge_active = false;
+    if (g->merge_status != CCU_OK) {
+        const int rc = g->merge_status;
+        g->merge_status = CCU_OK;
+        return fail(rc, "%s", g->merge_error.c_str());
+    }
+    return CCU_OK;
+}
+
+int ccu_group_render_merge_wait(ccu_group *g) {
+    if (!g) return fail(CCU_EINVAL, "ccu_group_render_merge_wait: null group");
+    std::unique_lock<std::mutex> lk(g->mu);
+    return join_group_merge(g, lk);
+}
+
+// reduce (if the window is still open), then start the read-back of every local share on its GPU's copy stream and hand the merge
+// to a worker; returns at once.  Caller holds g->mu through `lk`.
+static int group_merge_start(ccu_group *g, std::unique_lock<std::mutex> &lk, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp) {
+    int rc = join_group_merge(g, lk);          // one merge at a time: the share / staging buffers are about to be reused
+    if (rc != CCU_OK) return rc;
     if (g->window_total > 0) {
-        int rc = reduce_window_locked(g);
+        rc = reduce_window_locked(g);
         if (rc != CCU_OK) return rc;
     }
     const int total = g->reduced_total;
@@ -404,41 +441,69 @@ int ccu_group_render_merge(ccu_group *g, double *sample_buffer, int32_t sample_s
     if (total == 0) return CCU_OK;
     const int world = g->world;
     const size_t n_img = (size_t)g->width * g->height * 3;
-    // 3. every GPU reads its share back over its own PCIe link; the shares are merged into the sample buffer in parallel
+    // every GPU reads its share back over its own PCIe link
+    for (auto &m : g->local) {
+        ccu_ctx *c = m.ctx;
+        DeviceGuard dg(c->device);
+        const size_t lo = (size_t)m.rank * m.share_n, hi = std::min(n_img, lo + m.share_n);
+        CU(cudaEventRecord(c->window_ev, c->stream));
+        CU(cudaStreamWaitEvent(c->copy_stream, c->window_ev, 0));
+        if (lo < hi) {
+            rc = ccu_host::start_readback(c, m.share - lo, lo, hi, c->copy_stream);    // indexed by absolute float offset
+            if (rc != CCU_OK) return rc;
+        }
+    }
     //    sample = (sample * sample_spp + window_mean * total) / (sample_spp + total), window_mean = sum / total (or sum of means / world)
     const double ds = (double)sample_spp, sinv = 1.0 / (double)(sample_spp + total);
     const double dp = g->reduced_equal ? (double)total / (double)world : 1.0;
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const unsigned merge_threads = std::max(2u, hw / (unsigned)g->local.size());
-    std::vector<int> status(g->local.size(), CCU_OK);
-    std::vector<std::string> errors(g->local.size());
-    auto merge_one = [&](size_t i) {
-        Member &m = g->local[i];
-        ccu_ctx *c = m.ctx;
-        cudaSetDevice(c->device);
-        const size_t lo = (size_t)m.rank * m.share_n;
-        const size_t hi = std::min(n_img, lo + m.share_n);
-        const float *src = m.share - lo;                            // indexed by absolute float offset
-        int rc = lo < hi ? ccu_host::merge_window_range(c, src, lo, hi, sample_buffer, ds, dp, sinv, c->stream, merge_threads) : CCU_OK;
-        if (rc == CCU_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(CCU_ECUDA, "group merge: stream error");
-        if (rc != CCU_OK) { status[i] = rc; errors[i] = ccu_host::last_error(); }
-    };
-    if (g->local.size() == 1) {
-        merge_one(0);
-    } else {
-        std::vector<std::thread> th;
-        for (size_t i = 0; i < g->local.size(); i++) th.emplace_back(merge_one, i);
-        for (auto &t : th) t.join();
-    }
-    for (size_t i = 0; i < status.size(); i++)
-        if (status[i] != CCU_OK) return fail(status[i], "%s", errors[i].c_str());
     g->reduced_total = 0;
+    g->merge_active = true;
+    g->merge_status = CCU_OK;
+    g->merge_worker = std::thread([=] {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned merge_threads = std::max(2u, hw / (unsigned)g->local.size());
+        std::vector<int> status(g->local.size(), CCU_OK);
+        std::vector<std::string> errors(g->local.size());
+        auto merge_one = [&](size_t i) {
+            Member &m = g->local[i];
+            const size_t lo = (size_t)m.rank * m.share_n, hi = std::min(n_img, lo + m.share_n);
+            const int st = ccu_host::merge_readback(m.ctx, lo, hi, sample_buffer, ds, dp, sinv, merge_threads);
+            if (st != CCU_OK) { status[i] = st; errors[i] = ccu_host::last_error(); }
+        };
+        if (g->local.size() == 1) {
+            merge_one(0);
+        } else {
+            std::vector<std::thread> th;
+            for (size_t i = 0; i < g->local.size(); i++) th.emplace_back(merge_one, i);
+            for (auto &t : th) t.join();
+        }
+        for (size_t i = 0; i < status.size(); i++)
+            if (status[i] != CCU_OK) { g->merge_status = status[i]; g->merge_error = errors[i]; break; }
+    });
+    return CCU_OK;
+}
+
+int ccu_group_render_merge_async(ccu_group *g, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp) {
+    if (!g || !sample_buffer) return fail(CCU_EINVAL, "ccu_group_render_merge_async: null argument");
+    if (sample_spp < 0) return fail(CCU_EINVAL, "ccu_group_render_merge_async: negative spp");
+    std::unique_lock<std::mutex> lk(g->mu);
+    return group_merge_start(g, lk, sample_buffer, sample_spp, merged_spp);
+}
+
+int ccu_group_render_merge(ccu_group *g, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp) {
+    if (!g || !sample_buffer) return fail(CCU_EINVAL, "ccu_group_render_merge: null argument");
+    if (sample_spp < 0) return fail(CCU_EINVAL, "ccu_group_render_merge: negative spp");
+    std::unique_lock<std::mutex> lk(g->mu);
+    int rc = group_merge_start(g, lk, sample_buffer, sample_spp, merged_spp);
+    if (rc != CCU_OK) return rc;
+    rc = join_group_merge(g, lk);
+    if (rc != CCU_OK) return rc;
     return finish_reduce_timing(g);
 }
 
 int ccu_group_render_end(ccu_group *g) {
     if (!g) return fail(CCU_EINVAL, "ccu_group_render_end: null group");
-    int rc = CCU_OK;
+    int rc = ccu_group_render_merge_wait(g);
     for (auto &m : g->local) {
         const int r = ccu_render_end(m.ctx);
         if (rc == CCU_OK) rc = r;

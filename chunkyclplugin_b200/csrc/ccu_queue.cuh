@@ -74,7 +74,7 @@ constexpr int Q_TOP_WORDS = 4096;            // top tables up to 16^3 cells are 
 // word per entry and lane (entry k of lane l of warp w at word (k * Q_WARPS + w) * 32 + l: bank = lane, conflict free);
 // deeper entries, which a reasonable BVH never needs, go to local memory.
 #ifndef CCU_Q_STACK
-#define CCU_Q_STACK 20
+#define CCU_Q_STACK 16
 #endif
 constexpr int Q_SMEM_LIMIT = 227 * 1024 - 1280;   // dynamic shared memory a CTA may ask for, less the kernel's static tables (SmemTables)
 constexpr int Q_STACK = CCU_Q_STACK;
@@ -538,7 +538,10 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
 constexpr int Q_TILE_W = 32, Q_TILE_H = 32;
 constexpr unsigned Q_CHUNK = Q_TILE_W * Q_TILE_H;
 // k-th pixel in tile order (bands of Q_TILE_H rows, each cut into tiles Q_TILE_W wide, row-major inside a tile;
-// the last band / last tile of a band may be smaller): a bijection of [0, W*H) that keeps consecutive k close on screen
+// the last band / last tile of a band may be smaller): a bijection of [0, W*H) that keeps consecutive k close on screen.
+// PATCH: inside full 32x32 tiles, 32 consecutive k cover an 8x4 pixel patch instead of a 32x1 strip (thread-per-ray kernels:
+// a warp's rays then form a compact bundle).
+template <bool PATCH = false>
 __device__ __forceinline__ int tile_order_pixel(unsigned k, int W, int H) {
     const unsigned band_px = (unsigned)W * Q_TILE_H;
     const unsigned band = k / band_px;
@@ -554,8 +557,14 @@ __device__ __forceinline__ int tile_order_pixel(unsigned k, int W, int H) {
         tw = (unsigned)W - full_tiles * Q_TILE_W;
         in = kb - full_tiles * tile_px;
     }
-    const unsigned py = band * Q_TILE_H + in / tw;
-    const unsigned px = tile * Q_TILE_W + in % tw;
+    unsigned iy = in / tw, ix = in % tw;
+    if (PATCH && tw == Q_TILE_W && bh == Q_TILE_H) {
+        // in = [y4 y3 y2 | x4 x3 | y1 y0 | x2 x1 x0]
+        ix = (in & 7u) | (((in >> 5) & 3u) << 3);
+        iy = ((in >> 3) & 3u) | ((in >> 7) << 2);
+    }
+    const unsigned py = band * Q_TILE_H + iy;
+    const unsigned px = tile * Q_TILE_W + ix;
     return (int)(py * (unsigned)W + px);
 }
 

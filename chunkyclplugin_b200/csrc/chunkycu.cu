@@ -75,18 +75,24 @@ __device__ __forceinline__ int face_of(float3 n) {
     return 6;
 }
 
-// First-hit pass (BASELINE config 2): closestIntersect (kernel.h:14-24) for the camera ray of every pixel.  Pixels are taken in
-// 32x32 screen-tile order (tile_order_pixel: neighbouring lanes walk neighbouring rays, which keeps the warp converged
-// and its brick loads in the same cache lines); with the commit-time layouts (MODE 1 / 2) the march runs on the air layout and
-// the treeData index of the hit leaf (reference numbering, ClSceneLoader.java:56-59) is found by one root descent for the hit
-// voxel only.
-template <int MODE>
-__global__ void __launch_bounds__(256) k_first_hit(const __grid_constant__ DScene s, int seed, int n_pixels, int *block, int *face, int *node,
+// First-hit pass (BASELINE config 2): closestIntersect (kernel.h:14-24) for the camera ray of every pixel.
+// Pixels are taken in 32x32 screen tiles, 8x4 patches per warp (tile_order_pixel<true>: the lanes of a warp walk neighbouring
+// rays, which keeps their step counts and brick loads together).  With the commit-time layouts (MODE 1 / 2) the warp marches on
+// the air layout until every lane sits at a non-air leaf or has left the octree, THEN runs the block tests of all those lanes
+// together (the block test is ~3x the instructions of a march step; run per lane as each ray arrives it executed at 6 of 32
+// lanes), and repeats for the lanes whose block test missed.  The treeData index of the hit leaf (reference numbering,
+// ClSceneLoader.java:56-59) is found by one root descent for the hit voxel only.  HAS_BVH = false compiles the entity BVHs out.
+#ifndef CCU_FH_MIN_BLOCKS
+#define CCU_FH_MIN_BLOCKS 3
+#endif
+template <int MODE, bool HAS_BVH>
+__global__ void __launch_bounds__(256, CCU_FH_MIN_BLOCKS) k_first_hit(const __grid_constant__ DScene s, int seed, int n_pixels, int *block, int *face, int *node,
                                                    int *kind, float *t, float *normal, float *color) {
     stage_tables(s, nullptr);
+    const unsigned full = 0xffffffffu;
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= (unsigned)n_pixels) return;
-    const int gid = tile_order_pixel(k, s.width, s.height);
+    const bool valid = k < (unsigned)n_pixels;
+    const int gid = valid ? tile_order_pixel<true>(k, s.width, s.height) : 0;
     uint32_t rng = (uint32_t)seed + (uint32_t)gid;
     rng_next(rng);
     float3 o, d;
@@ -95,11 +101,51 @@ __global__ void __launch_bounds__(256) k_first_hit(const __grid_constant__ DScen
     rec.distance = inff_(); rec.material = 0; rec.surf.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
     rec.surf.color = make_float4(0, 0, 0, 0); rec.surf.emittance = 0;
     HitInfo hi = {-1, 0, 0, 0, 0};
-    bool hit = closest_intersect_mode<MODE>(s, o, d, rec, hi);
-    if (MODE != 0 && node && hit && hi.kind == 1) {
-        int level;
-        find_leaf(s, hi.bx, hi.by, hi.bz, level, hi.node);
+    bool hit = false;
+    if (MODE == 0) {
+        if (valid) hit = HAS_BVH ? closest_intersect_ref(s, o, d, rec, hi) : octree_intersect_ref(s, o, d, rec, hi);
+        if (!HAS_BVH && hit) rec.point = o + d * (rec.distance - CCU_OFFSET);
+    } else {
+        March m;
+        const bool entered = march_begin(s, m, o, d, rec.distance);
+        LeanRay r;
+        r.o = m.o; r.d = m.d; r.inv = m.inv; r.t = m.t; r.limit = m.limit; r.steps = m.steps;
+        lean_prepare(r);
+        int st = (valid && entered) ? 0 : 2;      // 0 marching, 1 at a non-air leaf, 2 left the octree without a hit, 3 hit
+        for (;;) {
+            while (__any_sync(full, st == 0)) {
+                if (st == 0) st = lean_probe<MODE == 2, false>(s, s.air_top, r);
+            }
+            if (st == 1) {
+                m.t = r.t; m.steps = r.steps;
+                const Cell c = march_cell(m);
+                int level;
+                const int data = find_leaf_wide(s, c.bx, c.by, c.bz, level);
+                float th;
+                if (march_block(s, m, data, level, rec.surf, th)) {
+                    rec.distance = th;
+                    rec.material = data;
+                    hi.kind = 1;
+                    hi.bx = c.bx; hi.by = c.by; hi.bz = c.bz;
+                    st = 3;
+                } else {
+                    r.t = m.t; r.steps = m.steps;
+                    st = 0;
+                }
+            }
+            if (!__any_sync(full, st == 0)) break;
+        }
+        hit = st == 3;
+        if (HAS_BVH && valid) {
+            int bk = 0;
+            if (bvh_pair(s, o, d, rec.distance, rec.surf, bk)) { hit = true; hi.kind = bk; }
+        }
+        if (node && hit && hi.kind == 1) {
+            int level;
+            find_leaf(s, hi.bx, hi.by, hi.bz, level, hi.node);
+        }
     }
+    if (!valid) return;
     if (block) block[gid] = hit ? rec.material : 0;
     if (face) face[gid] = hit ? face_of(rec.surf.normal) : 6;
     if (node) node[gid] = hit ? hi.node : -1;
@@ -122,7 +168,7 @@ __global__ void __launch_bounds__(256) k_preview(const __grid_constant__ DScene 
     stage_tables(s, nullptr);
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= (unsigned)n_pixels) return;
-    const int gid = tile_order_pixel(k, s.width, s.height);
+    const int gid = tile_order_pixel<true>(k, s.width, s.height);
     int W = s.width, H = s.height;
     int px = gid % W, py = gid / W;
     if ((px == W / 2 && (py >= H / 2 - 5 && py <= H / 2 + 5)) || (py == H / 2 && (px >= W / 2 - 5 && px <= W / 2 + 5))) {
@@ -951,10 +997,14 @@ static int render_passes_locked(ccu_ctx *c, const int32_t *seeds, int32_t n_pass
         qp.march_warps = bvh ? 64 : c->q_march_warps;   // with BVHs the service warps are the ones that do not walk
         const int lay = air_layout_id(c);
         const int grid = c->sm_count, block = Q_WARPS * 32;
-        // the sky table is staged in shared memory when it fits beside the path pool (128 x 128 texels = 64 KiB)
+        // The sky table is staged in shared memory when it is small: shared memory and L1 are one array on this chip, and a
+        // 128 x 128 table (64 KiB) taken from L1 costs more brick / atlas hits than the sky lookups gain (measured: +1.8 % per
+        // pass on config 1).  CCU_SKY_SMEM_MAX (bytes, default 16 KiB = 64 x 64 texels) moves the threshold.
         const int sky_texels = c->sky_res * c->sky_res;
         const int base_smem = q_smem_bytes(bvh, lay == 0);
-        const bool sky_smem = getenv("CCU_NO_SKY_SMEM") == nullptr && sky_texels <= 16384 && base_smem + sky_texels * 4 <= Q_SMEM_LIMIT;
+        const char *sky_env = getenv("CCU_SKY_SMEM_MAX");
+        const int sky_max = sky_env ? atoi(sky_env) : 16384;
+        const bool sky_smem = sky_texels * 4 <= sky_max && base_smem + sky_texels * 4 <= Q_SMEM_LIMIT;
         qp.sky_texels = sky_smem ? sky_texels : 0;
         const int smem = base_smem + qp.sky_texels * 4;
         if (bvh) {
@@ -1206,9 +1256,11 @@ int ccu_first_hit(ccu_ctx *c, int32_t seed, int32_t *block, int32_t *face, int32
     const int mode = layout_mode(c);
     const unsigned blocks = (unsigned)((n + 255) / 256);
     cudaEventRecord(c->ev0, c->stream);
-    if (mode == 0) k_first_hit<0><<<blocks, 256, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color);
-    else if (mode == 1) k_first_hit<1><<<blocks, 256, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color);
-    else k_first_hit<2><<<blocks, 256, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color);
+    const bool fh_bvh = !(c->scene.world_bvh_empty && c->scene.actor_bvh_empty);
+#define CCU_FH(M, B) k_first_hit<M, B><<<blocks, 256, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color)
+    if (fh_bvh) { if (mode == 0) CCU_FH(0, true); else if (mode == 1) CCU_FH(1, true); else CCU_FH(2, true); }
+    else { if (mode == 0) CCU_FH(0, false); else if (mode == 1) CCU_FH(1, false); else CCU_FH(2, false); }
+#undef CCU_FH
     c->launches++;
     cudaEventRecord(c->ev1, c->stream);
     if (c->projector_type == -1) cudaEventRecord(c->rays_used[c->rays_active], c->stream);

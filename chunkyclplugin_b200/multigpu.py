@@ -70,6 +70,11 @@ class SharedSampleBuffer:
             self.shm = shared_memory.SharedMemory(create=True, size=n_doubles * 8, name=name)
         else:
             self.shm = shared_memory.SharedMemory(name=name)
+            try:        # the creator unlinks it; keep this process's resource tracker from reporting it as leaked
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.owner = create
         self.array = np.ndarray((n_doubles,), dtype=np.float64, buffer=self.shm.buf)
         if create:
@@ -120,6 +125,13 @@ class SampleParallelRenderer:
         passes); returns the number of passes merged.  Collective in a one-process-per-GPU job."""
         return self.group.render_merge(sample_buffer, sample_spp)
 
-    def render_and_merge(self, seeds: Sequence[int], sample_buffer: np.ndarray, sample_spp: int) -> int:
+    def render_and_merge(self, seeds: Sequence[int], sample_buffer: np.ndarray, sample_spp: int, overlap: bool = False) -> int:
+        """``overlap``: return once the reduce-scatter and the share read-backs are queued - the next window renders while the
+        shares are merged (call ``finish()`` before reading the buffer)."""
         self.render_window(seeds, sync=False)
+        if overlap:
+            return self.group.render_merge_async(sample_buffer, sample_spp)
         return self.merge(sample_buffer, sample_spp)
+
+    def finish(self):
+        self.group.render_merge_wait()

@@ -98,6 +98,8 @@ SYMBOLS = {
     "ccu_group_render_passes": (C.c_int, [_vp, _vp, _i32]),
     "ccu_group_render_sync": (C.c_int, [_vp]),
     "ccu_group_render_merge": (C.c_int, [_vp, _vp, _i32, _pi32]),
+    "ccu_group_render_merge_async": (C.c_int, [_vp, _vp, _i32, _pi32]),
+    "ccu_group_render_merge_wait": (C.c_int, [_vp]),
     "ccu_group_render_reduce": (C.c_int, [_vp, _pi32]),
     "ccu_group_render_end": (C.c_int, [_vp]),
     "ccu_group_last_ms": (C.c_int, [_vp, C.POINTER(_f), C.POINTER(_f)]),
@@ -106,10 +108,28 @@ SYMBOLS = {
 _lib = None
 
 
+def _prefer_bundled_nccl():
+    """The multi-GPU entry points bind NCCL at run time (dlopen "libnccl.so.2").  A process shares ONE object of that soname,
+    whichever user loads it first; torch needs the (newer) copy it ships with, so point the library at that copy when it exists."""
+    if os.environ.get("CCU_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["CCU_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def load():
     """Load libchunkycu.so; raises OSError when it has not been built (the UnsatisfiedLinkError path)."""
     global _lib
     if _lib is None:
+        _prefer_bundled_nccl()
         if not os.path.exists(LIB_PATH):
             raise OSError(f"{LIB_PATH} not built - run `python -m chunkyclplugin_b200.build` (needs nvcc); there is no CPU fallback")
         lib = C.CDLL(LIB_PATH)
@@ -441,6 +461,17 @@ class Group:
         m = C.c_int32()
         check(self._lib.ccu_group_render_merge(self._h, _ptr(sample_buffer), sample_spp, C.byref(m)))
         return m.value
+
+    def render_merge_async(self, sample_buffer: np.ndarray, sample_spp: int) -> int:
+        assert sample_buffer.dtype == np.float64 and sample_buffer.flags.c_contiguous
+        m = C.c_int32()
+        check(self._lib.ccu_group_render_merge_async(self._h, _ptr(sample_buffer), sample_spp, C.byref(m)))
+        self._merge_keepalive = sample_buffer
+        return m.value
+
+    def render_merge_wait(self):
+        check(self._lib.ccu_group_render_merge_wait(self._h))
+        self._merge_keepalive = None
 
     def reduce_only(self) -> int:
         """Reduce-scatter of the open window without the read-back (the sums stay on the GPUs); returns the window's passes."""

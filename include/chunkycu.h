@@ -190,6 +190,10 @@ int ccu_group_render_sync(ccu_group *g);
 /* reduce-scatter of the window sums, per-GPU read-back of its share, merge into sample_buffer (all shares with ccu_group_create;
  * only this rank's share - sample_buffer must then be memory shared by all ranks - with ccu_group_join).  Collective. */
 int ccu_group_render_merge(ccu_group *g, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp);
+/* the same, returning once the reduce-scatter and the share read-backs are queued: the next window renders while the shares travel
+ * and are merged (sample_buffer stays in use until ccu_group_render_merge_wait / the next merge / ccu_group_render_end). */
+int ccu_group_render_merge_async(ccu_group *g, double *sample_buffer, int32_t sample_spp, int32_t *merged_spp);
+int ccu_group_render_merge_wait(ccu_group *g);
 /* only the device part of the merge: reduce-scatter of the open window (closes it; the sums stay on the GPUs until the next
  * ccu_group_render_merge reads them back).  *window_spp = passes of the window.  Collective. */
 int ccu_group_render_reduce(ccu_group *g, int32_t *window_spp);

@@ -16,6 +16,7 @@ import se.llbit.chunky.renderer.scene.Camera;
 import se.llbit.chunky.renderer.scene.Scene;
 import se.llbit.chunky.renderer.scene.Sky;
 import se.llbit.chunky.renderer.scene.SkyCache;
+import org.apache.commons.math3.util.FastMath;
 import se.llbit.math.Matrix3;
 import se.llbit.math.Ray;
 import se.llbit.math.Vector3;
@@ -115,12 +116,14 @@ public class CudaSceneLoader extends AbstractSceneLoader {
         int res = skyResolution(scene);
         byte[] texels = new byte[res * res * 4];
         Ray ray = new Ray();
-        for (int j = 0; j < res; j++) {
-            double phi = ((double) j / res) * Math.PI - Math.PI / 2;
-            double r = Math.cos(phi);
-            for (int i = 0; i < res; i++) {
-                double theta = ((double) i / res) * 2 * Math.PI;
-                ray.d.set(Math.cos(theta) * r, Math.sin(phi), Math.sin(theta) * r);
+        // FastMath and the i-outer / j-inner order of ClSky.java:43-58: the texel bytes are truncated, so the same
+        // transcendental implementation is needed to land on the same byte at a truncation edge
+        for (int i = 0; i < res; i++) {
+            for (int j = 0; j < res; j++) {
+                double theta = ((double) i / res) * 2 * FastMath.PI;
+                double phi = ((double) j / res) * FastMath.PI - FastMath.PI / 2;
+                double r = FastMath.cos(phi);
+                ray.d.set(FastMath.cos(theta) * r, FastMath.sin(phi), FastMath.sin(theta) * r);
                 scene.sky().getSkyColor(ray, false);
                 int at = 4 * (j * res + i);
                 texels[at] = (byte) (ray.color.x * 255);
@@ -147,7 +150,7 @@ public class CudaSceneLoader extends AbstractSceneLoader {
      * ClCamera.java:33-105: 15 floats for the pinhole projector (position - origin, row-major transform, aperture, subject
      * distance, fovTan), or 6 floats per pixel of rays generated by Chunky's own projector for every other projection mode.
      */
-    public void uploadCamera(Scene scene, Lock renderLock, boolean jitter) {
+    public boolean uploadCamera(Scene scene, Lock renderLock, boolean jitter) {      // returns ClCamera.needGenerate
         Camera camera = scene.camera();
         if (camera.getProjectionMode() == se.llbit.chunky.renderer.projection.ProjectionMode.PINHOLE) {
             Vector3 pos = new Vector3(camera.getPosition());
@@ -159,7 +162,7 @@ public class CudaSceneLoader extends AbstractSceneLoader {
             settings[13] = (float) camera.getSubjectDistance();
             settings[14] = (float) Camera.clampedFovTan(camera.getFov());
             ctx.cameraSet(0, settings);
-            return;
+            return false;
         }
         int w = scene.width, h = scene.height;
         float[] rays = new float[w * h * 6];
@@ -176,11 +179,10 @@ public class CudaSceneLoader extends AbstractSceneLoader {
                 System.arraycopy(Util.vector3ToFloat(ray.d), 0, rays, at + 3, 3);
             }
         });
-        if (renderLock != null) renderLock.lock();
-        try {
-            ctx.cameraSet(-1, rays);
-        } finally {
-            if (renderLock != null) renderLock.unlock();
-        }
+        // The reference takes renderLock around the upload because its command queue is shared with the pass loop
+        // (ClCamera.java:99-104).  ccu_camera_set uploads into the ray buffer no launch is reading, on the library's copy stream,
+        // so the upload overlaps the passes in flight and the next ccu_render_passes picks the new rays up: no lock needed.
+        ctx.cameraSet(-1, rays);
+        return true;
     }
 }

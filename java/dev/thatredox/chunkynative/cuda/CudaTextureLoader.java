@@ -6,7 +6,6 @@ import it.unimi.dsi.fastutil.objects.Object2ObjectMap;
 import se.llbit.chunky.resources.Texture;
 
 import java.util.ArrayList;
-import java.util.Comparator;
 import java.util.List;
 
 /**
@@ -32,41 +31,53 @@ public class CudaTextureLoader extends AbstractTextureLoader {
 
     @Override
     protected void buildTextures(Object2ObjectMap<Texture, TextureRecord> textures) {
+        // ClTextureLoader.java:32-44: stable sort by packed size, largest first; first fit scanning x outer / y inner over the layers
+        // in order; a new layer only when no existing one takes the texture
         List<Placed> all = new ArrayList<>();
         textures.forEach((t, r) -> all.add(new Placed(t, r)));
-        all.sort(Comparator.comparingInt((Placed p) -> p.size).reversed());
+        all.sort((a, b) -> b.size - a.size);
 
-        List<boolean[][]> used = new ArrayList<>();
+        List<boolean[][]> layers = new ArrayList<>();
+        layers.add(new boolean[TILES][TILES]);
         for (Placed p : all) {
-            int w = (p.width() + TILE - 1) / TILE, h = (p.height() + TILE - 1) / TILE;
-            boolean done = false;
-            for (int layer = 0; !done; layer++) {
-                if (layer == used.size()) used.add(new boolean[TILES][TILES]);
-                boolean[][] grid = used.get(layer);
-                for (int x = 0; x + w <= TILES && !done; x++)
-                    for (int y = 0; y + h <= TILES && !done; y++)
-                        if (free(grid, x, y, w, h)) {
-                            take(grid, x, y, w, h);
-                            p.x = x; p.y = y; p.layer = layer;
-                            done = true;
-                        }
+            if (!insert(layers, p)) {
+                layers.add(new boolean[TILES][TILES]);
+                insert(layers, p);
             }
         }
 
-        ctx.atlasCreate(TILES * TILE, TILES * TILE, Math.max(1, used.size()));
+        ctx.atlasCreate(TILES * TILE, TILES * TILE, layers.size());
         for (Placed p : all) {
             ctx.atlasWrite(p.x * TILE, p.y * TILE, p.layer, p.width(), p.height(), rgba8(p.texture));
-            p.record.set(((long) p.size << 32) | (((long) p.x << 22) | ((long) p.y << 13) | p.layer) & 0xFFFFFFFFL);
+            p.record.set(((long) p.size << 32) | (((long) p.x << 22) | ((long) p.y << 13) | p.layer) & 0xFFFFFFFFL);   // :123-132
         }
     }
 
-    private static boolean free(boolean[][] grid, int x, int y, int w, int h) {
-        for (int j = y; j < y + h; j++) for (int i = x; i < x + w; i++) if (grid[j][i]) return false;
-        return true;
+    /** ClTextureLoader.java:72-87: tile counts are width / 16 and height / 16, rounded DOWN, exactly as the reference reserves them. */
+    private static boolean insert(List<boolean[][]> layers, Placed p) {
+        int l = 0;
+        for (boolean[][] layer : layers) {
+            for (int x = 0; x < TILES; x++)
+                for (int y = 0; y < TILES; y++)
+                    if (insertAt(x, y, p.width() / TILE, p.height() / TILE, layer)) {
+                        p.x = x; p.y = y; p.layer = l;
+                        return true;
+                    }
+            l++;
+        }
+        return false;
     }
 
-    private static void take(boolean[][] grid, int x, int y, int w, int h) {
-        for (int j = y; j < y + h; j++) for (int i = x; i < x + w; i++) grid[j][i] = true;
+    /** ClTextureLoader.java:89-113 */
+    private static boolean insertAt(int x, int y, int width, int height, boolean[][] layer) {
+        if (y + height > layer.length || x + width > layer[0].length) return false;
+        for (int line = y; line < y + height; line++)
+            for (int pixel = x; pixel < x + width; pixel++)
+                if (layer[line][pixel]) return false;
+        for (int line = y; line < y + height; line++)
+            for (int pixel = x; pixel < x + width; pixel++)
+                layer[line][pixel] = true;
+        return true;
     }
 
     /** Linear float colour -> byte, truncating, as ClTextureLoader.java:154-168. */

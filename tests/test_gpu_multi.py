@@ -82,9 +82,14 @@ def test_two_gpu_group_matches_one_gpu(n_passes, scenes, cuda_ctx):
         render_ms, reduce_ms = group.last_ms()
         assert render_ms > 0 and reduce_ms > 0
         assert np.allclose(sb, want, rtol=2e-6, atol=1e-7)
-        # second window into the same buffer
-        group.render_passes(pass_seeds(n_passes + 4)[n_passes:])
-        assert group.render_merge(sb, 3 + n_passes) == 4
+        # second window into the same buffer, merged while a third one renders (ccu_group_render_merge_async)
+        more = pass_seeds(n_passes + 10)[n_passes:]
+        group.render_passes(more[:4])
+        assert group.render_merge_async(sb, 3 + n_passes) == 4
+        group.render_passes(more[4:])
+        group.render_merge_wait()
+        assert group.reduce_only() == 6          # device part only: the sums stay on the GPUs ...
+        assert group.render_merge(sb, 7 + n_passes) == 6     # ... until the next merge reads them back
         group.render_end()
     finally:
         group.close()
