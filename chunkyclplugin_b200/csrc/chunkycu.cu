@@ -83,7 +83,7 @@ __device__ __forceinline__ int face_of(float3 n) {
 // lanes), and repeats for the lanes whose block test missed.  The treeData index of the hit leaf (reference numbering,
 // ClSceneLoader.java:56-59) is found by one root descent for the hit voxel only.  HAS_BVH = false compiles the entity BVHs out.
 #ifndef CCU_FH_MIN_BLOCKS
-#define CCU_FH_MIN_BLOCKS 3
+#define CCU_FH_MIN_BLOCKS 4
 #endif
 template <int MODE, bool HAS_BVH>
 __global__ void __launch_bounds__(256, CCU_FH_MIN_BLOCKS) k_first_hit(const __grid_constant__ DScene s, int seed, int n_pixels, int *block, int *face, int *node,
