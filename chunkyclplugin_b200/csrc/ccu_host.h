@@ -81,6 +81,14 @@ struct MergeJob {
 
 }  // namespace ccu_host
 
+// BVH stage of the wavefront kernel: with walks that can be handed from warp to warp (CCU_BVH_PARK, ccu_queue.cuh) every warp may
+// walk; the round-1 form needed service warps that never do (23 of 28 walk)
+#if !defined(CCU_BVH_PARK) || CCU_BVH_PARK
+#define CCU_BVH_PARK_DEFAULT_WARPS 64
+#else
+#define CCU_BVH_PARK_DEFAULT_WARPS 23
+#endif
+
 struct ccu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;        // render stream
@@ -140,11 +148,12 @@ struct ccu_ctx {
     int *fh_scratch = nullptr;              // first-hit planes (kept between calls)
     size_t fh_scratch_pixels = 0;
     unsigned int *work_counter = nullptr;
+    int *bvh_deep = nullptr;                // wavefront kernel, BVH scenes: traversal-stack entries beyond the shared-memory part
     int yield_below = 20;
     int q_refill_min = 8;
     int q_march_bias = 4;
     int q_leaf_min = 12;
-    int q_bvh_warps = 23;
+    int q_bvh_warps = CCU_BVH_PARK_DEFAULT_WARPS;
     int q_march_warps = 22;
     int window_spp = 0;
     int closed_spp = 0;          // passes of the window closed by ccu_render_window_close, read-back in flight, not merged yet

@@ -3,6 +3,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdlib>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -59,9 +60,19 @@ unsigned wide_node(const int *tree, size_t n, int word, int lvl, WideLayout &b) 
 // lookup is one table load plus at most one brick load.
 struct AirLayout {
     std::vector<unsigned> top, wide, bricks;
+    std::vector<unsigned char> wide_level;     // level of every 64-ary node (its entries sit two levels below)
     int cell_level = 4, top_log2 = 0;
     bool ok = true;
 };
+
+// The top table is filled slab by slab (x ranges) on several host threads; every thread appends to vectors of its own, and the
+// indices it handed out are shifted by the sizes of the slabs before it when the parts are joined.
+inline int layout_threads(int dim) {
+    if (dim < 8) return 1;
+    if (const char *e = getenv("CCU_COMMIT_THREADS")) return std::max(1, std::min(dim, atoi(e)));
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min({hw ? hw : 4u, (unsigned)dim, 16u}));
+}
 
 inline unsigned air_leaf(int word, int level) { return CCU_WIDE_LEAF | ((word == 0 ? (unsigned)level : 31u) << 26); }
 inline int oct_child(int x, int y, int z) { return ((x & 1) << 2) | ((y & 1) << 1) | (z & 1); }
@@ -120,6 +131,7 @@ unsigned air_node(const int *tree, size_t n, int word, int lvl, AirLayout &b) {
     const size_t idx = b.wide.size() / 64;
     if (idx >= 0x1FFFFFFu) { b.ok = false; return air_leaf(1, 0); }
     b.wide.resize(b.wide.size() + 64);
+    b.wide_level.push_back((unsigned char)lvl);
     for (int i = 0; i < 4; i++)
         for (int j = 0; j < 4; j++)
             for (int k = 0; k < 4; k++) {
@@ -165,6 +177,24 @@ void air_small_brick(const int *tree, size_t n, int depth, AirLayout &b) {
             }
 }
 
+// cells [x0, x1) of the top table, into `b` (indices local to b)
+inline void air_fill_slab(const int *tree, size_t n, int depth, int cl, int dim, int x0, int x1, unsigned *top, AirLayout &b) {
+    for (int x = x0; x < x1 && b.ok; x++)
+        for (int y = 0; y < dim; y++)
+            for (int z = 0; z < dim; z++) {
+                int level = depth;
+                int word = tree[0];
+                while (word > 0 && level > cl) {
+                    level--;
+                    const int sh = level - cl;
+                    const size_t at = (size_t)word + oct_child(x >> sh, y >> sh, z >> sh);
+                    if (at >= n) { b.ok = false; word = 0; break; }
+                    word = tree[at];
+                }
+                top[((size_t)x * dim + y) * dim + z] = word <= 0 ? air_leaf(word, level) : air_node(tree, n, word, cl, b);
+            }
+}
+
 AirLayout build_air_layout(const int *tree, size_t n, int depth) {
     AirLayout b;
     if (depth < 4) {
@@ -180,20 +210,35 @@ AirLayout build_air_layout(const int *tree, size_t n, int depth) {
         b.top_log2 = depth - cl;
         const int dim = 1 << b.top_log2;
         b.top.assign((size_t)dim * dim * dim, 0u);
-        for (int x = 0; x < dim && b.ok; x++)
-            for (int y = 0; y < dim; y++)
-                for (int z = 0; z < dim; z++) {
-                    int level = depth;
-                    int word = tree[0];
-                    while (word > 0 && level > cl) {
-                        level--;
-                        const int sh = level - cl;
-                        const size_t at = (size_t)word + oct_child(x >> sh, y >> sh, z >> sh);
-                        if (at >= n) { b.ok = false; word = 0; break; }
-                        word = tree[at];
-                    }
-                    b.top[((size_t)x * dim + y) * dim + z] = word <= 0 ? air_leaf(word, level) : air_node(tree, n, word, cl, b);
+        const int nt = layout_threads(dim);
+        if (nt == 1) {
+            air_fill_slab(tree, n, depth, cl, dim, 0, dim, b.top.data(), b);
+        } else {
+            std::vector<AirLayout> part(nt);
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; t++)
+                th.emplace_back([&, t] { air_fill_slab(tree, n, depth, cl, dim, dim * t / nt, dim * (t + 1) / nt, b.top.data(), part[t]); });
+            for (auto &t : th) t.join();
+            for (int t = 0; t < nt; t++) {
+                const unsigned wide_off = (unsigned)(b.wide.size() / 64), brick_off = (unsigned)(b.bricks.size() / 256);
+                AirLayout &p = part[t];
+                b.ok = b.ok && p.ok;
+                // entries below the leaf bit are indices: of bricks where they sit at level 4, of 64-ary nodes above that
+                for (size_t j = 0; j < p.wide_level.size(); j++) {
+                    const unsigned off = p.wide_level[j] - 2 == 4 ? brick_off : wide_off;
+                    for (int e = 0; e < 64; e++)
+                        if (!(p.wide[j * 64 + e] & CCU_WIDE_LEAF)) p.wide[j * 64 + e] += off;
                 }
+                const unsigned top_off = cl == 4 ? brick_off : wide_off;
+                const size_t c0 = (size_t)(dim * t / nt) * dim * dim, c1 = (size_t)(dim * (t + 1) / nt) * dim * dim;
+                for (size_t c = c0; c < c1; c++)
+                    if (!(b.top[c] & CCU_WIDE_LEAF)) b.top[c] += top_off;
+                b.wide.insert(b.wide.end(), p.wide.begin(), p.wide.end());
+                b.wide_level.insert(b.wide_level.end(), p.wide_level.begin(), p.wide_level.end());
+                b.bricks.insert(b.bricks.end(), p.bricks.begin(), p.bricks.end());
+            }
+            if (b.wide.size() / 64 >= 0x1FFFFFFu || b.bricks.size() / 256 >= 0x7FFFFFu) b.ok = false;
+        }
     }
     if (b.wide.empty()) b.wide.assign(64, air_leaf(1, 0));
     if (b.bricks.empty()) b.bricks.assign(256, 0u);
@@ -255,17 +300,8 @@ int bvh_ref(const std::vector<int> &bvh, const std::vector<int> &trigs, size_t n
     return (int)r;
 }
 
-WideLayout build_wide_layout(const int *tree, size_t n, int depth) {
-    WideLayout b;
-    int cl = std::max(depth - 7, 4);
-    if (const char *e = getenv("CCU_CELL_LEVEL")) cl = std::max(0, atoi(e));   // tuning knob: level of the top table's cells
-    if (cl & 1) cl++;
-    if (cl > depth) cl = depth & ~1;
-    b.cell_level = cl;
-    b.top_log2 = depth - cl;
-    const int dim = 1 << b.top_log2;
-    b.top.assign((size_t)dim * dim * dim, 0u);
-    for (int x = 0; x < dim && b.ok; x++)
+inline void wide_fill_slab(const int *tree, size_t n, int depth, int cl, int dim, int x0, int x1, unsigned *top, WideLayout &b) {
+    for (int x = x0; x < x1 && b.ok; x++)
         for (int y = 0; y < dim; y++)
             for (int z = 0; z < dim; z++) {
                 int level = depth;
@@ -277,8 +313,42 @@ WideLayout build_wide_layout(const int *tree, size_t n, int depth) {
                     if (at >= n) { b.ok = false; word = 0; break; }
                     word = tree[at];
                 }
-                b.top[((size_t)x * dim + y) * dim + z] = word <= 0 ? wide_leaf(word, level, b.ok) : wide_node(tree, n, word, cl, b);
+                top[((size_t)x * dim + y) * dim + z] = word <= 0 ? wide_leaf(word, level, b.ok) : wide_node(tree, n, word, cl, b);
             }
+}
+
+WideLayout build_wide_layout(const int *tree, size_t n, int depth) {
+    WideLayout b;
+    int cl = std::max(depth - 7, 4);
+    if (const char *e = getenv("CCU_CELL_LEVEL")) cl = std::max(0, atoi(e));   // tuning knob: level of the top table's cells
+    if (cl & 1) cl++;
+    if (cl > depth) cl = depth & ~1;
+    b.cell_level = cl;
+    b.top_log2 = depth - cl;
+    const int dim = 1 << b.top_log2;
+    b.top.assign((size_t)dim * dim * dim, 0u);
+    const int nt = layout_threads(dim);
+    if (nt == 1) {
+        wide_fill_slab(tree, n, depth, cl, dim, 0, dim, b.top.data(), b);
+    } else {
+        std::vector<WideLayout> part(nt);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&, t] { wide_fill_slab(tree, n, depth, cl, dim, dim * t / nt, dim * (t + 1) / nt, b.top.data(), part[t]); });
+        for (auto &t : th) t.join();
+        for (int t = 0; t < nt; t++) {
+            const unsigned off = (unsigned)(b.wide.size() / 64);
+            WideLayout &p = part[t];
+            b.ok = b.ok && p.ok;
+            for (unsigned &e : p.wide)
+                if (!(e & CCU_WIDE_LEAF)) e += off;           // every index refers to a 64-ary node
+            const size_t c0 = (size_t)(dim * t / nt) * dim * dim, c1 = (size_t)(dim * (t + 1) / nt) * dim * dim;
+            for (size_t c = c0; c < c1; c++)
+                if (!(b.top[c] & CCU_WIDE_LEAF)) b.top[c] += off;
+            b.wide.insert(b.wide.end(), p.wide.begin(), p.wide.end());
+        }
+        if (b.wide.size() / 64 >= 0x7FFFFFFFu) b.ok = false;
+    }
     if (b.wide.empty()) b.wide.assign(64, wide_leaf(0, 0, b.ok));
     return b;
 }

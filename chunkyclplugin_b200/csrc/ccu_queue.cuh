@@ -48,7 +48,15 @@ static_assert(Q_ROWS >= 1 && Q_ROWS <= 64, "at most two mask words per stage and
 // QS_BVH / QS_SHADE exist only in the kernels built for scenes with entity BVHs (HAS_BVH): there the BVH traversal runs as
 // a stage of its own between the octree part of closestIntersect (BLOCK / EXIT) and the shading (SHADE); without BVHs
 // BLOCK / EXIT shade directly.
-enum QStage : int { QS_MARCH = 0, QS_BLOCK, QS_EXIT, QS_END, QS_BVH, QS_SHADE, QS_COUNT_BVH };
+// CCU_BVH_PARK (default): a BVH walk is a slot state like a marching ray - its traversal stack lives in shared memory by slot - so
+// walks can be handed from warp to warp: QS_BVH steps inner nodes for 32 walks that are all at inner nodes, QS_LEAF runs the
+// triangle tests for 32 walks that are all at leaves.  -DCCU_BVH_PARK=0 keeps the round-1 form (a walk stays in the registers
+// of the lane that started it; the warp alternates between inner turns and leaf turns).
+#ifndef CCU_BVH_PARK
+#define CCU_BVH_PARK 1
+#endif
+enum QStage : int { QS_MARCH = 0, QS_BLOCK, QS_EXIT, QS_END, QS_BVH, QS_SHADE, QS_LEAF, QS_COUNT_BVH_ALL };
+constexpr int QS_COUNT_BVH = CCU_BVH_PARK ? (int)QS_COUNT_BVH_ALL : (int)QS_LEAF;
 constexpr int QS_COUNT = QS_BVH;   // stages of the kernels without BVHs
 
 // Slot fields.  The running mean stays in the accumulation buffer (read-modify-write per sample, L2 only); the
@@ -61,7 +69,9 @@ enum QField : int {
     // HAS_BVH only: the closest hit so far while the ray is in the BVH / SHADE stages.  Its distance, emittance and normal.x
     // re-use the march fields of the (finished) ray: QF_LIMIT, QF_T, QF_STEPS.
     QF_HNY = QF_COUNT, QF_HNZ, QF_HCX, QF_HCY, QF_HCZ,
-    QF_COUNT_BVH,
+    QF_BREF, QF_BSP,        // CCU_BVH_PARK: the walk's next node and (stack entries | phase << 8)
+    QF_COUNT_BVH_ALL,
+    QF_COUNT_BVH = CCU_BVH_PARK ? (int)QF_COUNT_BVH_ALL : (int)QF_BREF,
     QF_HDIST = QF_LIMIT, QF_HEM = QF_T, QF_HNX = QF_STEPS
 };
 // QF_META: pass (bits 0..15) | ray depth (bits 16..23) | flags
@@ -71,14 +81,16 @@ constexpr uint32_t QM_HIT = 1u << 26;        // BVH / SHADE stages: the ray has 
 
 constexpr int Q_TOP_WORDS = 4096;            // top tables up to 16^3 cells are staged in shared memory
 // BVH stage: the first Q_STACK entries of a walk's traversal stack (bvh.h:38 nodesToVisit[64]) live in shared memory, one
-// word per entry and lane (entry k of lane l of warp w at word (k * Q_WARPS + w) * 32 + l: bank = lane, conflict free);
-// deeper entries, which a reasonable BVH never needs, go to local memory.
+// word per entry and owner (CCU_BVH_PARK: owner = slot, entry k at word k * Q_SLOTS + slot; otherwise owner = thread); bank =
+// lane column, conflict free.  Deeper entries, which a reasonable BVH never needs, go to a global scratch array (parked
+// walks) / local memory.
 #ifndef CCU_Q_STACK
 #define CCU_Q_STACK 16
 #endif
 constexpr int Q_SMEM_LIMIT = 227 * 1024 - 1280;   // dynamic shared memory a CTA may ask for, less the kernel's static tables (SmemTables)
 constexpr int Q_STACK = CCU_Q_STACK;
-constexpr int Q_STACK_WORDS = Q_STACK * Q_WARPS * 32;
+constexpr int Q_DEEP = 64 - Q_STACK;          // stack entries beyond the shared-memory part
+constexpr int Q_STACK_WORDS = Q_STACK * (CCU_BVH_PARK ? Q_SLOTS : Q_WARPS * 32);
 __host__ __device__ constexpr int q_fields(bool bvh) { return bvh ? (int)QF_COUNT_BVH : (int)QF_COUNT; }
 __host__ __device__ constexpr int q_stages(bool bvh) { return bvh ? (int)QS_COUNT_BVH : (int)QS_COUNT; }
 __host__ __device__ constexpr int q_mask_words(bool bvh) { return q_stages(bvh) * Q_MW * 32; }
@@ -116,6 +128,7 @@ struct QueueParams {
     int march_warps;   // scheduler: only warps 0 .. march_warps-1 run the MARCH stage
     int march_bias;    // scheduler: warps of sub-partitions 0..2 count MARCH columns +bias, warps of sub-partition 3 -bias
     int sky_texels;    // > 0: the launch reserved this many texels (4 bytes each) behind the other shared arrays for the sky table
+    int *bvh_deep;     // CCU_BVH_PARK: global scratch for traversal-stack entries beyond Q_STACK, Q_DEEP words per slot and CTA
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -146,6 +159,18 @@ __device__ __forceinline__ void q_push(unsigned *mask, int stage, int lane, int 
 }
 __device__ __forceinline__ bool q_has_work(const unsigned *mask, int stage, int lane) {
     return *(reinterpret_cast<const volatile qmask_t *>(mask) + stage * 32 + lane) != 0;
+}
+
+// start of kernel.h:17-18 / what follows a finished BVH: phase 0 = world BVH, 1 = actor BVH, 2 = both done
+__device__ __forceinline__ void bvh_first_ref(const DScene &s, int &ref, int &phase) {
+    ref = 0;
+    if (!s.world_bvh_empty) { phase = 0; ref = s.world_root; }
+    else if (!s.actor_bvh_empty) { phase = 1; ref = s.actor_root; }
+    else phase = 2;
+}
+__device__ __forceinline__ void bvh_phase_done(const DScene &s, int &ref, int &phase) {
+    if (phase == 0 && !s.actor_bvh_empty) { phase = 1; ref = s.actor_root; }
+    else { phase = 2; ref = 0; }
 }
 
 #define QI(f) (*reinterpret_cast<int *>(&F[(f) * Q_SLOTS + slot]))
@@ -344,7 +369,16 @@ __device__ __forceinline__ void q_stage_resolve(const DScene &s, uint32_t *F, un
         }
         const uint32_t meta = QU(QF_META);
         QU(QF_META) = ray_hit ? (meta | QM_HIT) : (meta & ~QM_HIT);
+#if CCU_BVH_PARK
+        // kernel.h:17-18: the world BVH first, then the actor BVH (the kernel is only launched when at least one is not empty)
+        int ref, phase;
+        bvh_first_ref(s, ref, phase);
+        QI(QF_BREF) = ref;
+        QI(QF_BSP) = phase << 8;
+        q_push(mask, ref < 0 ? QS_LEAF : QS_BVH, lane, row);
+#else
         q_push(mask, QS_BVH, lane, row);
+#endif
     } else {
         q_shade(s, F, mask, lane, row, m.o, m.d, distance, ray_hit, hit);
     }
@@ -405,6 +439,138 @@ __device__ __forceinline__ float triangle_hit_aligned(const int4 *__restrict__ t
     return nanf_();
 }
 
+#if CCU_BVH_PARK
+// traversal stack of the walk in `slot`: entry k
+__device__ __forceinline__ int *bvh_stack_entry(int *stk, int *deep, int slot, int k) {
+    return k < Q_STACK ? stk + k * Q_SLOTS + slot : deep + ((size_t)blockIdx.x * Q_SLOTS + slot) * Q_DEEP + (k - Q_STACK);
+}
+
+// QS_BVH: inner-node steps (bvh.h:73-108) for walks that sit at inner nodes.  Organised like MARCH: a lane keeps its walk in
+// registers while it steps from inner node to inner node; a walk that reaches a leaf or finishes is handed over (QS_LEAF /
+// QS_SHADE) and the lane takes the next waiting walk, in batches; a warp with too few walks parks them and switches stage.
+template <int NST>
+__device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsigned *mask, int *stk, int *deep, int lane, int yield_below, int refill_min) {
+    const unsigned full = 0xffffffffu;
+    int cur = -1;
+    float3 o = f3(0, 0, 0), inv = f3(0, 0, 0);
+    float dist = 0;
+    int ref = 0, sp = 0, phase = 2;
+    int busy = 0, n_fly = 0, recheck = 0;
+    for (;;) {
+        if (busy - n_fly >= refill_min || n_fly == 0) {
+            if (cur < 0 || phase >= 2 || ref < 0) {
+                if (cur >= 0) {
+                    F[QF_BREF * Q_SLOTS + cur] = (uint32_t)ref;
+                    F[QF_BSP * Q_SLOTS + cur] = (uint32_t)(sp | (phase << 8));
+                    q_push(mask, phase >= 2 ? QS_SHADE : QS_LEAF, cur & 31, cur >> 5);
+                }
+                const int row = q_pop(mask, QS_BVH, lane);
+                cur = row < 0 ? -1 : row * 32 + lane;
+                phase = 2; ref = 0;
+                if (cur >= 0) {
+                    const int slot = cur;
+                    o = f3(QFL(QF_OX), QFL(QF_OY), QFL(QF_OZ));
+                    inv = f3(QFL(QF_IX), QFL(QF_IY), QFL(QF_IZ));      // 1 / d, the same quotients bvh.h:40 computes
+                    dist = QFL(QF_HDIST);
+                    ref = QI(QF_BREF);
+                    const int bsp = QI(QF_BSP);
+                    sp = bsp & 0xFF;
+                    phase = bsp >> 8;
+                }
+            }
+            busy = __popc(__ballot_sync(full, cur >= 0));
+            if (busy == 0) return;
+            if (busy < yield_below) {
+                if (recheck == 0) {
+                    int best = 0;
+#pragma unroll
+                    for (int st = 0; st < NST; st++)
+                        if (st != QS_BVH) best = max(best, __popc(__ballot_sync(full, q_has_work(mask, st, lane))));
+                    if (best > busy) break;
+                    recheck = 4;
+                }
+                recheck--;
+            }
+        }
+        if (cur >= 0 && phase < 2 && ref >= 0) {
+            // inner node: both children's boxes (bvh.h:73-108)
+            const int4 *r = (phase == 0 ? s.world_rec : s.actor_rec) + (size_t)ref * 4;
+            const int4 a0 = __ldg(r), a1 = __ldg(r + 1), a2 = __ldg(r + 2), a3 = __ldg(r + 3);
+            const Box b1 = {i2f(a0.x), i2f(a0.y), i2f(a0.z), i2f(a0.w), i2f(a1.x), i2f(a1.y)};
+            const Box b2 = {i2f(a1.z), i2f(a1.w), i2f(a2.x), i2f(a2.y), i2f(a2.z), i2f(a2.w)};
+            const float t1 = box_entry(b1, o, inv);
+            const float t2 = box_entry(b2, o, inv);
+            const bool miss1 = is_nan(t1) || t1 > dist;
+            const bool miss2 = is_nan(t2) || t2 > dist;
+            const int left = a3.x, right = a3.y;
+            if (miss1 && miss2) {
+                if (sp == 0) bvh_phase_done(s, ref, phase);
+                else ref = *bvh_stack_entry(stk, deep, cur, --sp);
+            } else if (miss1) {
+                ref = right;
+            } else if (miss2) {
+                ref = left;
+            } else {
+                const bool near_left = t1 < t2;
+                *bvh_stack_entry(stk, deep, cur, sp++) = near_left ? right : left;
+                ref = near_left ? left : right;
+            }
+        }
+        n_fly = __popc(__ballot_sync(full, cur >= 0 && phase < 2 && ref >= 0));
+    }
+    // park the walks still at inner nodes, hand over the others
+    if (cur >= 0) {
+        F[QF_BREF * Q_SLOTS + cur] = (uint32_t)ref;
+        F[QF_BSP * Q_SLOTS + cur] = (uint32_t)(sp | (phase << 8));
+        q_push(mask, phase >= 2 ? QS_SHADE : (ref < 0 ? QS_LEAF : QS_BVH), cur & 31, cur >> 5);
+    }
+}
+#endif
+
+#if CCU_BVH_PARK
+// QS_LEAF: the triangles of one leaf (bvh.h:52-67) for walks that sit at a leaf, then the walk's next node from its stack
+__device__ __forceinline__ void q_stage_leaf(const DScene &s, uint32_t *F, unsigned *mask, int *stk, int *deep, int lane) {
+    const int row = q_pop(mask, QS_LEAF, lane);
+    QSTAT(20, 1); QSTAT(21, __popc(__ballot_sync(0xffffffffu, row >= 0)));
+    if (row < 0) return;
+    const int slot = row * 32 + lane;
+    const float3 o = f3(QFL(QF_OX), QFL(QF_OY), QFL(QF_OZ));
+    const float3 d = f3(QFL(QF_DX), QFL(QF_DY), QFL(QF_DZ));
+    float dist = QFL(QF_HDIST);
+    int ref = QI(QF_BREF);
+    const int bsp = QI(QF_BSP);
+    int sp = bsp & 0xFF, phase = bsp >> 8;
+    Surf hit;
+    hit.normal = f3(0, 0, 0); hit.color = make_float4(0, 0, 0, 0); hit.emittance = 0;
+    bool any = false;
+    const int4 *blk = s.tris2 + (-(ref + 1));
+    const int num = __ldg(blk).x;
+    for (int i = 0; i < num; i++) {
+        float3 normal;
+        float u, v;
+        int material;
+        const float t = triangle_hit_aligned(blk + 1 + 5 * i, dist, o, d, normal, u, v, material);
+        if (!is_nan(t) && material_sample(s, material, hit, u, v)) {
+            hit.normal = normal;
+            dist = t;
+            any = true;
+        }
+    }
+    if (any) {
+        // record->material keeps its octree value (bvh.h:59-65); nothing downstream reads it
+        QFL(QF_HDIST) = dist;
+        QFL(QF_HEM) = hit.emittance;
+        QFL(QF_HNX) = hit.normal.x; QFL(QF_HNY) = hit.normal.y; QFL(QF_HNZ) = hit.normal.z;
+        QFL(QF_HCX) = hit.color.x; QFL(QF_HCY) = hit.color.y; QFL(QF_HCZ) = hit.color.z;
+        QU(QF_META) |= QM_HIT;
+    }
+    if (sp == 0) bvh_phase_done(s, ref, phase);
+    else ref = *bvh_stack_entry(stk, deep, slot, --sp);
+    QI(QF_BREF) = ref;
+    QI(QF_BSP) = sp | (phase << 8);
+    q_push(mask, phase >= 2 ? QS_SHADE : (ref < 0 ? QS_LEAF : QS_BVH), lane, row);
+}
+#else
 struct BvhWalk {
     float3 o, d, inv;
     float dist;        // closest hit so far (record->distance)
@@ -534,6 +700,8 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
         n_done = __popc(__ballot_sync(full, cur >= 0 && b.phase >= 2));
     }
 }
+
+#endif   // CCU_BVH_PARK
 
 constexpr int Q_TILE_W = 32, Q_TILE_H = 32;
 constexpr unsigned Q_CHUNK = Q_TILE_W * Q_TILE_H;
@@ -667,7 +835,11 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
     unsigned *mask = q_mem + q_fields(HAS_BVH) * Q_SLOTS;
     int *live = reinterpret_cast<int *>(mask + MASK_WORDS);
     unsigned *top_s = mask + MASK_WORDS + 32;
+#if CCU_BVH_PARK
+    int *stk = reinterpret_cast<int *>(top_s + (LAY == 0 ? Q_TOP_WORDS : 0));                 // HAS_BVH only: stacks by slot
+#else
     int *stk = reinterpret_cast<int *>(top_s + (LAY == 0 ? Q_TOP_WORDS : 0)) + threadIdx.x;   // HAS_BVH only: this lane's stack column
+#endif
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
 
@@ -720,7 +892,12 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
             case QS_BLOCK:
             case QS_EXIT: q_stage_resolve<HAS_BVH>(s, F, mask, lane, best == QS_BLOCK); break;
             case QS_END: q_stage_end(s, qp.w, F, mask, live, lane); break;
+#if CCU_BVH_PARK
+            case QS_BVH: QSTAT(16, 1); if (HAS_BVH) q_stage_bvh<NST>(s, F, mask, stk, qp.bvh_deep, lane, qp.yield_below, qp.refill_min); break;
+            case QS_LEAF: if (HAS_BVH) q_stage_leaf(s, F, mask, stk, qp.bvh_deep, lane); break;
+#else
             case QS_BVH: QSTAT(16, 1); if (HAS_BVH) q_stage_bvh(s, F, mask, stk, lane, qp.refill_min, qp.leaf_min); break;
+#endif
             default: if (HAS_BVH) q_stage_shade(s, F, mask, lane); break;
         }
         __syncwarp();

@@ -628,6 +628,7 @@ int ccu_ctx_destroy(ccu_ctx *c) {
         if (c->seeds_pinned) cudaFreeHost(c->seeds_pinned);
         for (auto &e : c->seeds_ev) if (e) cudaEventDestroy(e);
         if (c->fh_scratch) cudaFree(c->fh_scratch);
+        if (c->bvh_deep) cudaFree(c->bvh_deep);
         if (c->work_counter) cudaFree(c->work_counter);
         if (c->unorm) cudaFree(c->unorm);
         for (auto &e : c->chunk_ev) if (e) cudaEventDestroy(e);
@@ -1006,6 +1007,14 @@ static int render_passes_locked(ccu_ctx *c, const int32_t *seeds, int32_t n_pass
         const int sky_max = sky_env ? atoi(sky_env) : 16384;
         const bool sky_smem = sky_texels * 4 <= sky_max && base_smem + sky_texels * 4 <= Q_SMEM_LIMIT;
         qp.sky_texels = sky_smem ? sky_texels : 0;
+        qp.bvh_deep = nullptr;
+#if CCU_BVH_PARK
+        if (bvh) {
+            // scratch for traversal-stack entries beyond the shared-memory part (bvh.h:38 allows 64 pending nodes)
+            if (!c->bvh_deep) CU(cudaMalloc(&c->bvh_deep, (size_t)c->sm_count * Q_SLOTS * Q_DEEP * sizeof(int)));
+            qp.bvh_deep = c->bvh_deep;
+        }
+#endif
         const int smem = base_smem + qp.sky_texels * 4;
         if (bvh) {
             if (lay == 0) k_render_queue<true, 0><<<grid, block, smem, c->stream>>>(c->scene, qp);
@@ -1240,6 +1249,7 @@ int ccu_first_hit(ccu_ctx *c, int32_t seed, int32_t *block, int32_t *face, int32
     if (c->fh_scratch_pixels < n) {
         cudaStreamSynchronize(c->stream);
         if (c->fh_scratch) cudaFree(c->fh_scratch);
+        if (c->bvh_deep) cudaFree(c->bvh_deep);
         c->fh_scratch = nullptr;
         c->fh_scratch_pixels = 0;
         CU(cudaMalloc(&c->fh_scratch, n * 12 * sizeof(int)));
