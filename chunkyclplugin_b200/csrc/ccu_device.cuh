@@ -63,10 +63,11 @@ struct DScene {
     const int *__restrict__ trigs;
     int world_bvh_empty, actor_bvh_empty;   // result of the bvh.h:23-32 probe, evaluated once at commit
     // BVH stage layout (built at commit): 64-byte records {left box, right box, left ref, right ref, pad, pad} per inner
-    // node, 16-byte aligned triangle blocks {count, 0, 0, 0} + count x 20 words; ref >= 0 record, ref < 0: -(1 + block offset / 4)
+    // node (two 256-bit loads), 32-byte aligned triangle blocks {count, 0 x 7} + count x 24 words (PackedTriangle's 20 words +
+    // pad: three 256-bit loads per triangle); ref >= 0 record, ref < 0: -(1 + block offset / 8 words)
     const int4 *__restrict__ world_rec;
     const int4 *__restrict__ actor_rec;
-    const int4 *__restrict__ tris2;
+    const int *__restrict__ tris2;
     int world_root, actor_root;
     // atlas: RGBA8, tile-linear (16x16 texel tiles contiguous), clamp extents = image extents
     const uchar4 *__restrict__ atlas;

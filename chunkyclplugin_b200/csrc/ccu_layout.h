@@ -248,21 +248,25 @@ AirLayout build_air_layout(const int *tree, size_t n, int depth) {
 // Traversal layout of a packed BVH (PackedBvhNode.java:22-31: 7 ints per node, first child at node + 7, second child at
 // node[0]) for the BVH stage of ccu_queue.cuh: one 64-byte record per inner node holding BOTH children's boxes
 // (bvh.h:73-91 fetches exactly those at every inner node) and a reference per child, and 16-byte aligned triangle
-// blocks.  ref >= 0: record index; ref < 0: leaf, -(1 + offset of its block in `tris`, in units of 4 words).
+// blocks.  ref >= 0: record index; ref < 0: leaf, -(1 + offset of its block in `tris`, in units of 8 words).
 struct BvhLayout {
     std::vector<int> rec;
     int root = 0;
     bool ok = true;
 };
 struct TriRepack {
-    std::vector<int> tris;                       // per leaf: {count, 0, 0, 0} + count x 20 words (PackedTriangle.java:46-78)
+    std::vector<int> tris;                       // per leaf: {count, 0 x 7} + count x (20 words (PackedTriangle.java:46-78) + 4 pad)
     int add(const std::vector<int> &trigs, int prim, bool &ok) {
         if (prim < 0 || (size_t)prim >= trigs.size()) { ok = false; return 0; }
         const int count = trigs[(size_t)prim];
         if (count < 0 || (size_t)prim + 1 + (size_t)count * 20 > trigs.size()) { ok = false; return 0; }
-        const int off = (int)(tris.size() / 4);
-        tris.push_back(count); tris.push_back(0); tris.push_back(0); tris.push_back(0);
-        tris.insert(tris.end(), trigs.begin() + prim + 1, trigs.begin() + prim + 1 + (size_t)count * 20);
+        const int off = (int)(tris.size() / 8);      // in units of 32 bytes
+        tris.push_back(count);
+        tris.insert(tris.end(), 7, 0);
+        for (int i = 0; i < count; i++) {
+            tris.insert(tris.end(), trigs.begin() + prim + 1 + (size_t)i * 20, trigs.begin() + prim + 1 + (size_t)(i + 1) * 20);
+            tris.insert(tris.end(), 4, 0);
+        }
         return off;
     }
 };

@@ -114,6 +114,16 @@ __device__ __forceinline__ float dm_acos(float x) {
     return 1.5707963267948966f - dm_asin(x);
 }
 
+// 256-bit read-only global load (LDG.E.256 on sm_100a): one instruction and one L1 tag lookup per lane for a 32-byte record half
+struct __align__(32) Int8 { int v[8]; };
+__device__ __forceinline__ Int8 ldg256(const void *p) {
+    Int8 r;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+
 // PCG hash RNG: randomness.h:6-17
 __device__ __forceinline__ uint32_t rng_next(uint32_t &state) {
     uint32_t s = state * 47796405u + 2891336453u;

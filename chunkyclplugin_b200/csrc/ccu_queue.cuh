@@ -85,7 +85,7 @@ constexpr int Q_TOP_WORDS = 4096;            // top tables up to 16^3 cells are 
 // lane column, conflict free.  Deeper entries, which a reasonable BVH never needs, go to a global scratch array (parked
 // walks) / local memory.
 #ifndef CCU_Q_STACK
-#define CCU_Q_STACK 16
+#define CCU_Q_STACK 12
 #endif
 constexpr int Q_SMEM_LIMIT = 227 * 1024 - 1280;   // dynamic shared memory a CTA may ask for, less the kernel's static tables (SmemTables)
 constexpr int Q_STACK = CCU_Q_STACK;
@@ -403,13 +403,13 @@ __device__ __forceinline__ void q_stage_shade(const DScene &s, uint32_t *F, unsi
 // ------------------------------------------------------------------------------------------------------
 // BVH stage: bvh.h:22-113 for the world BVH, then the actor BVH (kernel.h:17-18), on the commit-time layout
 // ------------------------------------------------------------------------------------------------------
-// Triangle_intersect (primitives.h:335-409) on an aligned 20-word record
-__device__ __forceinline__ float triangle_hit_aligned(const int4 *__restrict__ t, float distance, float3 origin, float3 dir, float3 &normal,
+// Triangle_intersect (primitives.h:335-409) on a 32-byte aligned 24-word record (20 words + pad), three 256-bit loads
+__device__ __forceinline__ float triangle_hit_aligned(const int *__restrict__ t, float distance, float3 origin, float3 dir, float3 &normal,
                                                       float &ou, float &ov, int &material) {
-    const int4 q0 = __ldg(t), q1 = __ldg(t + 1);
-    const int flags = q0.x;
-    const float3 e1 = f3(i2f(q0.y), i2f(q0.z), i2f(q0.w));
-    const float3 e2 = f3(i2f(q1.x), i2f(q1.y), i2f(q1.z));
+    const Int8 q0 = ldg256(t);
+    const int flags = q0.v[0];
+    const float3 e1 = f3(i2f(q0.v[1]), i2f(q0.v[2]), i2f(q0.v[3]));
+    const float3 e2 = f3(i2f(q0.v[4]), i2f(q0.v[5]), i2f(q0.v[6]));
     float3 pvec = cross3(dir, e2);
     float det = dot3(e1, pvec);
     if ((flags >> 8) & 1) {
@@ -418,8 +418,8 @@ __device__ __forceinline__ float triangle_hit_aligned(const int4 *__restrict__ t
         return nanf_();
     }
     float recip = 1.0f / det;
-    const int4 q2 = __ldg(t + 2);
-    float3 o = f3(i2f(q1.w), i2f(q2.x), i2f(q2.y));
+    const Int8 q1 = ldg256(t + 8);
+    float3 o = f3(i2f(q0.v[7]), i2f(q1.v[0]), i2f(q1.v[1]));
     float3 tvec = origin - o;
     float u = dot3(tvec, pvec) * recip;
     if (u < 0 || u > 1) return nanf_();
@@ -428,12 +428,13 @@ __device__ __forceinline__ float triangle_hit_aligned(const int4 *__restrict__ t
     if (v < 0 || (u + v) > 1) return nanf_();
     float tt = dot3(e2, qvec) * recip;
     if (tt > CCU_EPS && tt < distance) {
-        const int4 q3 = __ldg(t + 3), q4 = __ldg(t + 4);
+        const Int8 q2 = ldg256(t + 16);
         float w = 1.0f - u - v;
-        ou = (i2f(q3.y) * u + i2f(q3.w) * v) + i2f(q4.y) * w;
-        ov = (i2f(q3.z) * u + i2f(q4.x) * v) + i2f(q4.z) * w;
-        normal = f3(i2f(q2.z), i2f(q2.w), i2f(q3.x));
-        material = q4.w;
+        // words 13..18: t1.uv, t2.uv, t3.uv; 19: material
+        ou = (i2f(q1.v[5]) * u + i2f(q1.v[7]) * v) + i2f(q2.v[1]) * w;
+        ov = (i2f(q1.v[6]) * u + i2f(q2.v[0]) * v) + i2f(q2.v[2]) * w;
+        normal = f3(i2f(q1.v[2]), i2f(q1.v[3]), i2f(q1.v[4]));
+        material = q2.v[3];
         return tt;
     }
     return nanf_();
@@ -495,14 +496,14 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
         if (cur >= 0 && phase < 2 && ref >= 0) {
             // inner node: both children's boxes (bvh.h:73-108)
             const int4 *r = (phase == 0 ? s.world_rec : s.actor_rec) + (size_t)ref * 4;
-            const int4 a0 = __ldg(r), a1 = __ldg(r + 1), a2 = __ldg(r + 2), a3 = __ldg(r + 3);
-            const Box b1 = {i2f(a0.x), i2f(a0.y), i2f(a0.z), i2f(a0.w), i2f(a1.x), i2f(a1.y)};
-            const Box b2 = {i2f(a1.z), i2f(a1.w), i2f(a2.x), i2f(a2.y), i2f(a2.z), i2f(a2.w)};
+            const Int8 lo = ldg256(r), hi = ldg256(r + 2);
+            const Box b1 = {i2f(lo.v[0]), i2f(lo.v[1]), i2f(lo.v[2]), i2f(lo.v[3]), i2f(lo.v[4]), i2f(lo.v[5])};
+            const Box b2 = {i2f(lo.v[6]), i2f(lo.v[7]), i2f(hi.v[0]), i2f(hi.v[1]), i2f(hi.v[2]), i2f(hi.v[3])};
             const float t1 = box_entry(b1, o, inv);
             const float t2 = box_entry(b2, o, inv);
             const bool miss1 = is_nan(t1) || t1 > dist;
             const bool miss2 = is_nan(t2) || t2 > dist;
-            const int left = a3.x, right = a3.y;
+            const int left = hi.v[4], right = hi.v[5];
             if (miss1 && miss2) {
                 if (sp == 0) bvh_phase_done(s, ref, phase);
                 else ref = *bvh_stack_entry(stk, deep, cur, --sp);
@@ -543,13 +544,13 @@ __device__ __forceinline__ void q_stage_leaf(const DScene &s, uint32_t *F, unsig
     Surf hit;
     hit.normal = f3(0, 0, 0); hit.color = make_float4(0, 0, 0, 0); hit.emittance = 0;
     bool any = false;
-    const int4 *blk = s.tris2 + (-(ref + 1));
-    const int num = __ldg(blk).x;
+    const int *blk = s.tris2 + (size_t)(-(ref + 1)) * 8;
+    const int num = __ldg(blk);
     for (int i = 0; i < num; i++) {
         float3 normal;
         float u, v;
         int material;
-        const float t = triangle_hit_aligned(blk + 1 + 5 * i, dist, o, d, normal, u, v, material);
+        const float t = triangle_hit_aligned(blk + 8 + 24 * i, dist, o, d, normal, u, v, material);
         if (!is_nan(t) && material_sample(s, material, hit, u, v)) {
             hit.normal = normal;
             dist = t;
@@ -648,13 +649,13 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
         if (leaf_turn) {
             if (walking && b.ref < 0) {
                 // leaf: bvh.h:52-67
-                const int4 *blk = s.tris2 + (-(b.ref + 1));
-                const int num = __ldg(blk).x;
+                const int *blk = s.tris2 + (size_t)(-(b.ref + 1)) * 8;
+                const int num = __ldg(blk);
                 for (int i = 0; i < num; i++) {
                     float3 normal;
                     float u, v;
                     int material;
-                    const float dist = triangle_hit_aligned(blk + 1 + 5 * i, b.dist, b.o, b.d, normal, u, v, material);
+                    const float dist = triangle_hit_aligned(blk + 8 + 24 * i, b.dist, b.o, b.d, normal, u, v, material);
                     if (!is_nan(dist) && material_sample(s, material, b.hit, u, v)) {
                         b.hit.normal = normal;
                         b.dist = dist;
@@ -666,14 +667,14 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
         } else if (walking && b.ref >= 0) {
             // inner node: both children's boxes (bvh.h:73-108)
             const int4 *r = (b.phase == 0 ? s.world_rec : s.actor_rec) + (size_t)b.ref * 4;
-            const int4 a0 = __ldg(r), a1 = __ldg(r + 1), a2 = __ldg(r + 2), a3 = __ldg(r + 3);
-            const Box b1 = {i2f(a0.x), i2f(a0.y), i2f(a0.z), i2f(a0.w), i2f(a1.x), i2f(a1.y)};
-            const Box b2 = {i2f(a1.z), i2f(a1.w), i2f(a2.x), i2f(a2.y), i2f(a2.z), i2f(a2.w)};
+            const Int8 lo = ldg256(r), hi = ldg256(r + 2);
+            const Box b1 = {i2f(lo.v[0]), i2f(lo.v[1]), i2f(lo.v[2]), i2f(lo.v[3]), i2f(lo.v[4]), i2f(lo.v[5])};
+            const Box b2 = {i2f(lo.v[6]), i2f(lo.v[7]), i2f(hi.v[0]), i2f(hi.v[1]), i2f(hi.v[2]), i2f(hi.v[3])};
             const float t1 = box_entry(b1, b.o, b.inv);
             const float t2 = box_entry(b2, b.o, b.inv);
             const bool miss1 = is_nan(t1) || t1 > b.dist;
             const bool miss2 = is_nan(t2) || t2 > b.dist;
-            const int left = a3.x, right = a3.y;
+            const int left = hi.v[4], right = hi.v[5];
             if (miss1) {
                 if (miss2) pop = true;
                 else b.ref = right;

@@ -315,7 +315,7 @@ void fill_scene(ccu_ctx *c) {
     s.air_top_log2 = c->air_top_log2;
     s.world_rec = reinterpret_cast<const int4 *>(c->world_rec.p);
     s.actor_rec = reinterpret_cast<const int4 *>(c->actor_rec.p);
-    s.tris2 = reinterpret_cast<const int4 *>(c->tris2.p);
+    s.tris2 = c->tris2.p;
     s.world_root = c->world_root;
     s.actor_root = c->actor_root;
     s.block_palette = c->block_palette.p;
@@ -1249,7 +1249,6 @@ int ccu_first_hit(ccu_ctx *c, int32_t seed, int32_t *block, int32_t *face, int32
     if (c->fh_scratch_pixels < n) {
         cudaStreamSynchronize(c->stream);
         if (c->fh_scratch) cudaFree(c->fh_scratch);
-        if (c->bvh_deep) cudaFree(c->bvh_deep);
         c->fh_scratch = nullptr;
         c->fh_scratch_pixels = 0;
         CU(cudaMalloc(&c->fh_scratch, n * 12 * sizeof(int)));
