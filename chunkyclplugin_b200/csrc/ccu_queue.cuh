@@ -441,9 +441,21 @@ __device__ __forceinline__ float triangle_hit_aligned(const int *__restrict__ t,
 }
 
 #if CCU_BVH_PARK
-// traversal stack of the walk in `slot`: entry k
-__device__ __forceinline__ int *bvh_stack_entry(int *stk, int *deep, int slot, int k) {
-    return k < Q_STACK ? stk + k * Q_SLOTS + slot : deep + ((size_t)blockIdx.x * Q_SLOTS + slot) * Q_DEEP + (k - Q_STACK);
+// traversal stack of the walk in `slot` (bvh.h:38): entry k < Q_STACK in shared memory, the rest (which a reasonable BVH never
+// needs) in a global scratch array, out of line so that the common path is a compare and one shared-memory access
+static __device__ __noinline__ void bvh_deep_store(int *deep, int slot, int k, int value) {
+    deep[((size_t)blockIdx.x * Q_SLOTS + slot) * Q_DEEP + (k - Q_STACK)] = value;
+}
+static __device__ __noinline__ int bvh_deep_load(const int *deep, int slot, int k) {
+    return deep[((size_t)blockIdx.x * Q_SLOTS + slot) * Q_DEEP + (k - Q_STACK)];
+}
+__device__ __forceinline__ void bvh_stack_push(int *stk, int *deep, int slot, int k, int value) {
+    if (__builtin_expect(k < Q_STACK, 1)) stk[k * Q_SLOTS + slot] = value;
+    else bvh_deep_store(deep, slot, k, value);
+}
+__device__ __forceinline__ int bvh_stack_pop(int *stk, int *deep, int slot, int k) {
+    if (__builtin_expect(k < Q_STACK, 1)) return stk[k * Q_SLOTS + slot];
+    return bvh_deep_load(deep, slot, k);
 }
 
 // QS_BVH: inner-node steps (bvh.h:73-108) for walks that sit at inner nodes.  Organised like MARCH: a lane keeps its walk in
@@ -504,17 +516,15 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
             const bool miss1 = is_nan(t1) || t1 > dist;
             const bool miss2 = is_nan(t2) || t2 > dist;
             const int left = hi.v[4], right = hi.v[5];
-            if (miss1 && miss2) {
+            // bvh.h:93-108: both missed -> next pending node; one hit -> that child; both hit -> the nearer one, the other is
+            // left pending.  Written with selects so that only the stack accesses themselves are divergent.
+            const bool both = !miss1 && !miss2, none = miss1 && miss2;
+            const bool go_left = both ? t1 < t2 : !miss1;
+            if (both) bvh_stack_push(stk, deep, cur, sp++, go_left ? right : left);
+            ref = go_left ? left : right;
+            if (none) {
                 if (sp == 0) bvh_phase_done(s, ref, phase);
-                else ref = *bvh_stack_entry(stk, deep, cur, --sp);
-            } else if (miss1) {
-                ref = right;
-            } else if (miss2) {
-                ref = left;
-            } else {
-                const bool near_left = t1 < t2;
-                *bvh_stack_entry(stk, deep, cur, sp++) = near_left ? right : left;
-                ref = near_left ? left : right;
+                else ref = bvh_stack_pop(stk, deep, cur, --sp);
             }
         }
         n_fly = __popc(__ballot_sync(full, cur >= 0 && phase < 2 && ref >= 0));
@@ -566,7 +576,7 @@ __device__ __forceinline__ void q_stage_leaf(const DScene &s, uint32_t *F, unsig
         QU(QF_META) |= QM_HIT;
     }
     if (sp == 0) bvh_phase_done(s, ref, phase);
-    else ref = *bvh_stack_entry(stk, deep, slot, --sp);
+    else ref = bvh_stack_pop(stk, deep, slot, --sp);
     QI(QF_BREF) = ref;
     QI(QF_BSP) = sp | (phase << 8);
     q_push(mask, phase >= 2 ? QS_SHADE : (ref < 0 ? QS_LEAF : QS_BVH), lane, row);
