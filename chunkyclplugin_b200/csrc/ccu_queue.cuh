@@ -449,13 +449,17 @@ static __device__ __noinline__ void bvh_deep_store(int *deep, int slot, int k, i
 static __device__ __noinline__ int bvh_deep_load(const int *deep, int slot, int k) {
     return deep[((size_t)blockIdx.x * Q_SLOTS + slot) * Q_DEEP + (k - Q_STACK)];
 }
-__device__ __forceinline__ void bvh_stack_push(int *stk, int *deep, int slot, int k, int value) {
-    if (__builtin_expect(k < Q_STACK, 1)) stk[k * Q_SLOTS + slot] = value;
-    else bvh_deep_store(deep, slot, k, value);
+// `on`: this lane pushes / pops (the others pass through without a branch: the shared-memory access is a predicated instruction,
+// the out-of-line deep path a branch no lane of a reasonable BVH ever takes)
+__device__ __forceinline__ void bvh_stack_push(int *stk, int *deep, int slot, int k, int value, bool on) {
+    if (on && k < Q_STACK) stk[k * Q_SLOTS + slot] = value;
+    if (on && k >= Q_STACK) bvh_deep_store(deep, slot, k, value);
 }
-__device__ __forceinline__ int bvh_stack_pop(int *stk, int *deep, int slot, int k) {
-    if (__builtin_expect(k < Q_STACK, 1)) return stk[k * Q_SLOTS + slot];
-    return bvh_deep_load(deep, slot, k);
+__device__ __forceinline__ int bvh_stack_pop(int *stk, int *deep, int slot, int k, bool on, int otherwise) {
+    int v = otherwise;
+    if (on && k < Q_STACK) v = stk[k * Q_SLOTS + slot];
+    if (on && k >= Q_STACK) v = bvh_deep_load(deep, slot, k);
+    return v;
 }
 
 // QS_BVH: inner-node steps (bvh.h:73-108) for walks that sit at inner nodes.  Organised like MARCH: a lane keeps its walk in
@@ -520,12 +524,13 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
             // left pending.  Written with selects so that only the stack accesses themselves are divergent.
             const bool both = !miss1 && !miss2, none = miss1 && miss2;
             const bool go_left = both ? t1 < t2 : !miss1;
-            if (both) bvh_stack_push(stk, deep, cur, sp++, go_left ? right : left);
+            bvh_stack_push(stk, deep, cur, sp, go_left ? right : left, both);
+            sp += both ? 1 : 0;
             ref = go_left ? left : right;
-            if (none) {
-                if (sp == 0) bvh_phase_done(s, ref, phase);
-                else ref = bvh_stack_pop(stk, deep, cur, --sp);
-            }
+            const bool pop = none && sp > 0;
+            sp -= pop ? 1 : 0;
+            ref = bvh_stack_pop(stk, deep, cur, sp, pop, ref);
+            if (none && !pop) bvh_phase_done(s, ref, phase);
         }
         n_fly = __popc(__ballot_sync(full, cur >= 0 && phase < 2 && ref >= 0));
     }
@@ -576,7 +581,7 @@ __device__ __forceinline__ void q_stage_leaf(const DScene &s, uint32_t *F, unsig
         QU(QF_META) |= QM_HIT;
     }
     if (sp == 0) bvh_phase_done(s, ref, phase);
-    else ref = bvh_stack_pop(stk, deep, slot, --sp);
+    else { sp--; ref = bvh_stack_pop(stk, deep, slot, sp, true, ref); }
     QI(QF_BREF) = ref;
     QI(QF_BSP) = sp | (phase << 8);
     q_push(mask, phase >= 2 ? QS_SHADE : (ref < 0 ? QS_LEAF : QS_BVH), lane, row);
