@@ -40,9 +40,6 @@ constexpr int Q_WARPS = CCU_Q_WARPS;       // warps per CTA (one CTA per SM)
 constexpr int Q_ROWS = CCU_Q_ROWS;         // slots per lane column
 constexpr int Q_SLOTS = Q_ROWS * 32;
 constexpr int Q_MW = (Q_ROWS + 31) / 32;   // 32-bit words per work mask (one mask per stage and column; 64-bit masks for > 32 rows)
-template <int MW> struct QMaskType { typedef unsigned type; };
-template <> struct QMaskType<2> { typedef unsigned long long type; };
-typedef QMaskType<Q_MW>::type qmask_t;
 static_assert(Q_ROWS >= 1 && Q_ROWS <= 64, "at most two mask words per stage and column");
 
 // QS_BVH / QS_SHADE exist only in the kernels built for scenes with entity BVHs (HAS_BVH): there the BVH traversal runs as
@@ -127,38 +124,47 @@ struct QueueParams {
     int bvh_warps;     // scheduler: only warps 0 .. bvh_warps-1 run the BVH stage
     int march_warps;   // scheduler: only warps 0 .. march_warps-1 run the MARCH stage
     int march_bias;    // scheduler: warps of sub-partitions 0..2 count MARCH columns +bias, warps of sub-partition 3 -bias
+    int shade_min;     // scheduler: a warp holds back from a shading stage with fewer ready columns than this (a few rounds at most)
     int sky_texels;    // > 0: the launch reserved this many texels (4 bytes each) behind the other shared arrays for the sky table
     int *bvh_deep;     // CCU_BVH_PARK: global scratch for traversal-stack entries beyond Q_STACK, Q_DEEP words per slot and CTA
 };
 
 // ------------------------------------------------------------------------------------------------------
-// work masks: one qmask_t per stage and column, word index stage * 32 + column, bit = row
+// work masks: per stage and column a bit per row
 // ------------------------------------------------------------------------------------------------------
 // Lowest set bit first: warps that pop the same stage at the same time contend for the same rows, and the winner
 // takes (most of) a row across all columns.  Rows therefore tend to stay together from stage to stage, which keeps
 // the batches full; spreading the warps over different rows (measured) fragments the batches and is slower.
+// Masks are 32-bit words (shared-memory atomics are native on 32 bits): Q_MW words per stage and column, word w holds rows
+// 32 w .. 32 w + 31, at index (stage * Q_MW + w) * 32 + column.
 __device__ __forceinline__ int q_pop(unsigned *mask, int stage, int lane) {
-    qmask_t *word = reinterpret_cast<qmask_t *>(mask) + stage * 32 + lane;
-    qmask_t m = *reinterpret_cast<volatile qmask_t *>(word);
-    while (m) {
-        const qmask_t bit = m & (qmask_t(0) - m);
-        const qmask_t old = atomicAnd(word, ~bit);
-        QSTAT_LANE(14, 1);
-        if (old & bit) {
-            __threadfence_block();
-            return (Q_MW > 1 ? __ffsll((long long)bit) : __ffs((int)bit)) - 1;
+#pragma unroll
+    for (int w = 0; w < Q_MW; w++) {
+        unsigned *word = mask + (stage * Q_MW + w) * 32 + lane;
+        unsigned m = *reinterpret_cast<volatile unsigned *>(word);
+        while (m) {
+            const unsigned bit = m & (0u - m);
+            const unsigned old = atomicAnd(word, ~bit);
+            QSTAT_LANE(14, 1);
+            if (old & bit) {
+                __threadfence_block();
+                return w * 32 + __ffs((int)bit) - 1;
+            }
+            QSTAT_LANE(15, 1);
+            m = old & ~bit;
         }
-        QSTAT_LANE(15, 1);
-        m = old & ~bit;
     }
     return -1;
 }
 __device__ __forceinline__ void q_push(unsigned *mask, int stage, int lane, int row) {
     __threadfence_block();
-    atomicOr(reinterpret_cast<qmask_t *>(mask) + stage * 32 + lane, qmask_t(1) << row);
+    atomicOr(mask + (stage * Q_MW + (Q_MW > 1 ? row >> 5 : 0)) * 32 + lane, 1u << (row & 31));
 }
 __device__ __forceinline__ bool q_has_work(const unsigned *mask, int stage, int lane) {
-    return *(reinterpret_cast<const volatile qmask_t *>(mask) + stage * 32 + lane) != 0;
+    unsigned any = 0;
+#pragma unroll
+    for (int w = 0; w < Q_MW; w++) any |= *(reinterpret_cast<const volatile unsigned *>(mask) + (stage * Q_MW + w) * 32 + lane);
+    return any != 0;
 }
 
 // start of kernel.h:17-18 / what follows a finished BVH: phase 0 = world BVH, 1 = actor BVH, 2 = both done
@@ -860,8 +866,12 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
     const int lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < Q_SLOTS; i += blockDim.x) F[QF_META * Q_SLOTS + i] = QM_NEEDPIX;
-    for (int i = threadIdx.x; i < NST * 32; i += blockDim.x)
-        reinterpret_cast<qmask_t *>(mask)[i] = (i / 32 == QS_END) ? (Q_ROWS == 8 * (int)sizeof(qmask_t) ? ~qmask_t(0) : ((qmask_t(1) << Q_ROWS) - 1)) : qmask_t(0);
+    for (int i = threadIdx.x; i < NST * Q_MW * 32; i += blockDim.x) {
+        // every slot starts in the END stage (QM_NEEDPIX: it fetches its first pixel there)
+        const int st = i / (Q_MW * 32), w = (i / 32) % Q_MW;
+        const int rows_here = min(32, Q_ROWS - 32 * w);
+        mask[i] = st == QS_END ? (rows_here >= 32 ? 0xffffffffu : ((1u << rows_here) - 1u)) : 0u;
+    }
     if (LAY == 0) {
         const int n = 1 << (3 * s.air_top_log2);
         for (int i = threadIdx.x; i < n; i += blockDim.x) top_s[i] = __ldg(s.air_top + i);
@@ -882,6 +892,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
     __syncthreads();
     const unsigned *top = LAY == 0 ? top_s : s.air_top;
 
+    int held = 0;
     for (;;) {
         // the stage with the most columns that have work
         int best = -1, best_n = 0;
@@ -903,6 +914,13 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
             __nanosleep(100);
             continue;
         }
+        // thin shading batches cost a whole pass over the stage's code for a few paths: hold back a little for a fuller one
+        if (best != QS_MARCH && best_n < qp.shade_min && held < 3) {
+            held++;
+            __nanosleep(60);
+            continue;
+        }
+        held = 0;
         switch (best) {
             case QS_MARCH: QSTAT(0, 1); q_stage_march<NST, LAY>(s, top, F, mask, lane, qp.yield_below, qp.refill_min); break;
             case QS_BLOCK:

@@ -581,6 +581,7 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     if (const char *e = getenv("CCU_Q_LEAF_MIN")) c->q_leaf_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_Q_MARCH_BIAS")) c->q_march_bias = std::max(-32, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_Q_REFILL_MIN")) c->q_refill_min = std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("CCU_Q_SHADE_MIN")) c->q_shade_min = std::max(0, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_YIELD_BELOW")) c->yield_below = std::max(0, std::min(33, atoi(e)));
     DeviceGuard g(device_index);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -993,6 +994,7 @@ static int render_passes_locked(ccu_ctx *c, const int32_t *seeds, int32_t n_pass
         qp.yield_below = c->yield_below;
         qp.refill_min = c->q_refill_min;
         qp.march_bias = c->q_march_bias;
+        qp.shade_min = c->q_shade_min;
         qp.leaf_min = c->q_leaf_min;
         qp.bvh_warps = c->q_bvh_warps;
         qp.march_warps = bvh ? 64 : c->q_march_warps;   // with BVHs the service warps are the ones that do not walk
