@@ -124,7 +124,7 @@ struct QueueParams {
     int bvh_warps;     // scheduler: only warps 0 .. bvh_warps-1 run the BVH stage
     int march_warps;   // scheduler: only warps 0 .. march_warps-1 run the MARCH stage
     int march_bias;    // scheduler: warps of sub-partitions 0..2 count MARCH columns +bias, warps of sub-partition 3 -bias
-    int shade_min;     // scheduler: a warp holds back from a shading stage with fewer ready columns than this (a few rounds at most)
+    int shade_min;     // one-shot stages: a warp that got fewer slots than this puts them back and retries (q_pop_batch)
     int sky_texels;    // > 0: the launch reserved this many texels (4 bytes each) behind the other shared arrays for the sky table
     int *bvh_deep;     // CCU_BVH_PARK: global scratch for traversal-stack entries beyond Q_STACK, Q_DEEP words per slot and CTA
 };
@@ -142,8 +142,18 @@ __device__ __forceinline__ int q_pop(unsigned *mask, int stage, int lane) {
     for (int w = 0; w < Q_MW; w++) {
         unsigned *word = mask + (stage * Q_MW + w) * 32 + lane;
         unsigned m = *reinterpret_cast<volatile unsigned *>(word);
+#ifdef CCU_Q_FAIR
+        // experiment: the preferred row rotates with the SM clock (all warps of the SM agree on it, so rows still travel
+        // together), instead of row 0 always being served first
+        const unsigned rot = (unsigned)(clock() >> CCU_Q_FAIR) & 31u;
+#endif
         while (m) {
+#ifdef CCU_Q_FAIR
+            const unsigned mr = __funnelshift_r(m, m, rot);
+            const unsigned bit = 1u << ((__ffs((int)mr) - 1 + rot) & 31u);
+#else
             const unsigned bit = m & (0u - m);
+#endif
             const unsigned old = atomicAnd(word, ~bit);
             QSTAT_LANE(14, 1);
             if (old & bit) {
@@ -165,6 +175,22 @@ __device__ __forceinline__ bool q_has_work(const unsigned *mask, int stage, int 
 #pragma unroll
     for (int w = 0; w < Q_MW; w++) any |= *(reinterpret_cast<const volatile unsigned *>(mask) + (stage * Q_MW + w) * 32 + lane);
     return any != 0;
+}
+
+// One slot per lane for a one-shot stage.  Several warps often decide for the same stage at the same moment (they all saw the
+// same masks); the late ones find most columns already taken and would run the stage's whole code for a handful of paths.
+// With min_lanes > 1 such a warp puts its slots back and returns -2 on every lane (the scheduler retries a moment later,
+// with min_lanes = 1 after two such rounds, so that the last paths of a launch are never held up).
+__device__ __forceinline__ int q_pop_batch(unsigned *mask, int stage, int lane, int min_lanes) {
+    const int row = q_pop(mask, stage, lane);
+    if (min_lanes > 1) {
+        const int got = __popc(__ballot_sync(0xffffffffu, row >= 0));
+        if (got < min_lanes) {
+            if (row >= 0) q_push(mask, stage, lane, row);
+            return -2;
+        }
+    }
+    return row;
 }
 
 // start of kernel.h:17-18 / what follows a finished BVH: phase 0 = world BVH, 1 = actor BVH, 2 = both done
@@ -337,10 +363,11 @@ __device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *
 // BLOCK (kind_block = true) and EXIT (false): the octree part of closestIntersect (kernel.h:14-16) is finished here;
 // without BVHs the ray is shaded right away, with BVHs it goes to the BVH stage.  kind_block is warp-uniform.
 template <bool HAS_BVH>
-__device__ __forceinline__ void q_stage_resolve(const DScene &s, uint32_t *F, unsigned *mask, int lane, const bool kind_block) {
-    const int row = q_pop(mask, kind_block ? QS_BLOCK : QS_EXIT, lane);
+__device__ __forceinline__ bool q_stage_resolve(const DScene &s, uint32_t *F, unsigned *mask, int lane, const bool kind_block, int min_lanes) {
+    const int row = q_pop_batch(mask, kind_block ? QS_BLOCK : QS_EXIT, lane, min_lanes);
+    if (row == -2) return false;
     QSTAT(2 * (kind_block ? QS_BLOCK : QS_EXIT), 1); QSTAT(2 * (kind_block ? QS_BLOCK : QS_EXIT) + 1, __popc(__ballot_sync(0xffffffffu, row >= 0)));
-    if (row < 0) return;
+    if (row < 0) return true;
     const int slot = row * 32 + lane;
     March m;
     m.o = f3(QFL(QF_OX), QFL(QF_OY), QFL(QF_OZ));
@@ -360,7 +387,7 @@ __device__ __forceinline__ void q_stage_resolve(const DScene &s, uint32_t *F, un
         if (!march_block(s, m, data, level, hit, hit_t)) {
             QFL(QF_T) = m.t; QI(QF_STEPS) = m.steps;
             q_push(mask, QS_MARCH, lane, row);
-            return;
+            return true;
         }
         ray_hit = true;
     }
@@ -388,13 +415,15 @@ __device__ __forceinline__ void q_stage_resolve(const DScene &s, uint32_t *F, un
     } else {
         q_shade(s, F, mask, lane, row, m.o, m.d, distance, ray_hit, hit);
     }
+    return true;
 }
 
 // SHADE (HAS_BVH kernels): closestIntersect is complete (kernel.h:17-22)
-__device__ __forceinline__ void q_stage_shade(const DScene &s, uint32_t *F, unsigned *mask, int lane) {
-    const int row = q_pop(mask, QS_SHADE, lane);
+__device__ __forceinline__ bool q_stage_shade(const DScene &s, uint32_t *F, unsigned *mask, int lane, int min_lanes) {
+    const int row = q_pop_batch(mask, QS_SHADE, lane, min_lanes);
+    if (row == -2) return false;
     QSTAT(22, 1); QSTAT(23, __popc(__ballot_sync(0xffffffffu, row >= 0)));
-    if (row < 0) return;
+    if (row < 0) return true;
     const int slot = row * 32 + lane;
     const float3 o = f3(QFL(QF_OX), QFL(QF_OY), QFL(QF_OZ));
     const float3 d = f3(QFL(QF_DX), QFL(QF_DY), QFL(QF_DZ));
@@ -404,6 +433,7 @@ __device__ __forceinline__ void q_stage_shade(const DScene &s, uint32_t *F, unsi
     hit.color = make_float4(QFL(QF_HCX), QFL(QF_HCY), QFL(QF_HCZ), 0.0f);
     hit.emittance = QFL(QF_HEM);
     q_shade(s, F, mask, lane, row, o, d, QFL(QF_HDIST), ray_hit, hit);
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -551,10 +581,11 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
 
 #if CCU_BVH_PARK
 // QS_LEAF: the triangles of one leaf (bvh.h:52-67) for walks that sit at a leaf, then the walk's next node from its stack
-__device__ __forceinline__ void q_stage_leaf(const DScene &s, uint32_t *F, unsigned *mask, int *stk, int *deep, int lane) {
-    const int row = q_pop(mask, QS_LEAF, lane);
+__device__ __forceinline__ bool q_stage_leaf(const DScene &s, uint32_t *F, unsigned *mask, int *stk, int *deep, int lane, int min_lanes) {
+    const int row = q_pop_batch(mask, QS_LEAF, lane, min_lanes);
+    if (row == -2) return false;
     QSTAT(20, 1); QSTAT(21, __popc(__ballot_sync(0xffffffffu, row >= 0)));
-    if (row < 0) return;
+    if (row < 0) return true;
     const int slot = row * 32 + lane;
     const float3 o = f3(QFL(QF_OX), QFL(QF_OY), QFL(QF_OZ));
     const float3 d = f3(QFL(QF_DX), QFL(QF_DY), QFL(QF_DZ));
@@ -591,6 +622,7 @@ __device__ __forceinline__ void q_stage_leaf(const DScene &s, uint32_t *F, unsig
     QI(QF_BREF) = ref;
     QI(QF_BSP) = sp | (phase << 8);
     q_push(mask, phase >= 2 ? QS_SHADE : (ref < 0 ? QS_LEAF : QS_BVH), lane, row);
+    return true;
 }
 #else
 struct BvhWalk {
@@ -759,9 +791,10 @@ __device__ __forceinline__ int tile_order_pixel(unsigned k, int W, int H) {
 }
 
 // rayTracer.cl:109-112, then the next pass / pixel: rayTracer.cl:55-91
-__device__ __forceinline__ void q_stage_end(const DScene &s, const PassParams &w, uint32_t *F, unsigned *mask, int *live, int lane) {
+__device__ __forceinline__ bool q_stage_end(const DScene &s, const PassParams &w, uint32_t *F, unsigned *mask, int *live, int lane, int min_lanes) {
     const unsigned full = 0xffffffffu;
-    const int row = q_pop(mask, QS_END, lane);
+    const int row = q_pop_batch(mask, QS_END, lane, min_lanes);
+    if (row == -2) return false;
     QSTAT(2 * QS_END, 1); QSTAT(2 * QS_END + 1, __popc(__ballot_sync(full, row >= 0)));
     const int slot = row < 0 ? lane : row * 32 + lane;
     uint32_t meta = row >= 0 ? QU(QF_META) : 0u;
@@ -830,7 +863,7 @@ __device__ __forceinline__ void q_stage_end(const DScene &s, const PassParams &w
     }
     const unsigned died = __ballot_sync(full, row >= 0 && !alive);
     if (died && lane == (__ffs((int)died) - 1)) atomicSub(live, __popc(died));
-    if (!alive) return;
+    if (!alive) return true;
     // new sample
     QI(QF_GID) = gid;
     QU(QF_META) = (uint32_t)pass;   // ray depth 0, no flags
@@ -844,6 +877,7 @@ __device__ __forceinline__ void q_stage_end(const DScene &s, const PassParams &w
     March m;
     const bool entered = march_begin(s, m, o, d, inff_());
     q_store_ray(F, mask, lane, row, m, entered);
+    return true;
 }
 
 // LAY 0: the top table of the air layout fits Q_TOP_WORDS and is staged in shared memory; 1: it is read from global memory;
@@ -914,25 +948,26 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
             __nanosleep(100);
             continue;
         }
-        // thin shading batches cost a whole pass over the stage's code for a few paths: hold back a little for a fuller one
-        if (best != QS_MARCH && best_n < qp.shade_min && held < 3) {
-            held++;
-            __nanosleep(60);
-            continue;
-        }
-        held = 0;
+        const int min_lanes = held < 2 ? qp.shade_min : 1;      // see q_pop_batch
+        bool ran = true;
         switch (best) {
             case QS_MARCH: QSTAT(0, 1); q_stage_march<NST, LAY>(s, top, F, mask, lane, qp.yield_below, qp.refill_min); break;
             case QS_BLOCK:
-            case QS_EXIT: q_stage_resolve<HAS_BVH>(s, F, mask, lane, best == QS_BLOCK); break;
-            case QS_END: q_stage_end(s, qp.w, F, mask, live, lane); break;
+            case QS_EXIT: ran = q_stage_resolve<HAS_BVH>(s, F, mask, lane, best == QS_BLOCK, min_lanes); break;
+            case QS_END: ran = q_stage_end(s, qp.w, F, mask, live, lane, min_lanes); break;
 #if CCU_BVH_PARK
             case QS_BVH: QSTAT(16, 1); if (HAS_BVH) q_stage_bvh<NST>(s, F, mask, stk, qp.bvh_deep, lane, qp.yield_below, qp.refill_min); break;
-            case QS_LEAF: if (HAS_BVH) q_stage_leaf(s, F, mask, stk, qp.bvh_deep, lane); break;
+            case QS_LEAF: if (HAS_BVH) ran = q_stage_leaf(s, F, mask, stk, qp.bvh_deep, lane, min_lanes); break;
 #else
             case QS_BVH: QSTAT(16, 1); if (HAS_BVH) q_stage_bvh(s, F, mask, stk, lane, qp.refill_min, qp.leaf_min); break;
 #endif
-            default: if (HAS_BVH) q_stage_shade(s, F, mask, lane); break;
+            default: if (HAS_BVH) ran = q_stage_shade(s, F, mask, lane, min_lanes); break;
+        }
+        if (ran) {
+            held = 0;
+        } else {
+            held++;
+            __nanosleep(40);
         }
         __syncwarp();
     }
