@@ -221,7 +221,9 @@ CCU_MATERIAL_INLINE MatOut material_eval_core(const DScene &s, uint32_t flags, u
         out.color.x *= t.x; out.color.y *= t.y; out.color.z *= t.z; out.color.w *= t.w;
     }
     if (flags & 2u) out.emittance = atlas_read_uv(s, u, v, (int)normal_emittance, (int)tex_size).w;
-    else out.emittance = (float)((double)(normal_emittance & 0xFF) / 255.0);   // double literal in the reference (material.h:79)
+    // material.h:79 divides by the double literal 255.0: (float)((double)b / 255.0) == (float)b / 255.0f for all 256 byte values
+    // (checked exhaustively, tests/test_oracle_kat.py), i.e. the UNORM table entry - no fp64 division on the device
+    else out.emittance = smem_tables().unorm[normal_emittance & 0xFF];
     out.ok = 1;
     return out;
 }

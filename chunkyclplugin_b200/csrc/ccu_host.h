@@ -153,6 +153,7 @@ struct ccu_ctx {
     int q_refill_min = 8;
     int q_march_bias = 4;
     int q_shade_min = 0;
+    int q_sticky_min = 0;      // 0 = default by kernel (CCU_Q_STICKY)
     int q_leaf_min = 12;
     int q_bvh_warps = CCU_BVH_PARK_DEFAULT_WARPS;
     int q_march_warps = 22;

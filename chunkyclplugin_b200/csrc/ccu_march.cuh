@@ -92,6 +92,39 @@ __device__ __forceinline__ int lean_probe(const DScene &s, const unsigned *__res
     return 0;
 }
 
+// The same iteration as straight-line code for the shallow layouts (top table over 16^3 cells + bricks): every lane of the warp
+// executes every instruction, lanes without a ray in flight (`active` false) or whose ray ends compute on harmless values and
+// commit nothing.  No branch inside the step means no divergence stacks, no fetch redirects and one load latency per iteration
+// for the whole warp; the lanes whose cell is a single leaf read brick word 0 (one broadcast sector) instead of skipping the load.
+// `done`: the lane's state before the step (only read when !active); returns the state after it.
+template <bool TOPS>
+__device__ __forceinline__ int lean_step_flat(const DScene &s, const unsigned *__restrict__ top, LeanRay &r, bool active, int done) {
+    const bool fin0 = r.steps >= s.draw_depth || r.t > r.limit;
+    const float3 pos = r.o + r.d * r.t;
+    const float3 q = pos + r.doff;
+    const int bx = f2i(floorf(q.x)), by = f2i(floorf(q.y)), bz = f2i(floorf(q.z));
+    const bool fin = fin0 || (((bx | by | bz) >> s.depth) != 0);
+    const int tl = s.air_top_log2;
+    // out-of-cube coordinates (finished lanes only) are folded into the table
+    const unsigned ti = (((((unsigned)(bx >> 4) << tl) + (unsigned)(by >> 4)) << tl) + (unsigned)(bz >> 4)) & ((1u << (3 * tl)) - 1u);
+    const unsigned e = TOPS ? top[ti] : __ldg(top + ti);
+    const bool leaf = (e & CCU_WIDE_LEAF) != 0;
+    const unsigned wi = (unsigned)(((bx & 12) << 4) | ((by & 12) << 2) | (bz & 12) | (bx & 3));
+    const unsigned w = __ldg(s.air_bricks + (leaf ? 0u : e * 256u + wi));
+    const int code = (int)((w >> ((((by & 3) << 2) | (bz & 3)) * 2)) & 3u);
+    const int lvl_brick = w >= CCU_BRICK_UNIFORM ? (int)(w & 31u) : code - 1;
+    const int level = leaf ? ((int)(e << 1)) >> 27 : lvl_brick;       // -1 = not air
+    const int low = (1 << (level & 31)) - 1;
+    const float ex = lean_exit_axis(bx, low, r.fmx, q.x, r.inv.x);
+    const float ey = lean_exit_axis(by, low, r.fmy, q.y, r.inv.y);
+    const float ez = lean_exit_axis(bz, low, r.fmz, q.z, r.inv.z);
+    const float tn = r.t + (fminf(ex, fminf(ey, ez)) + CCU_OFFSET);
+    const bool adv = active && !fin && level >= 0;
+    r.t = adv ? tn : r.t;
+    r.steps += adv ? 1 : 0;
+    return active ? (fin ? 2 : (level < 0 ? 1 : 0)) : done;
+}
+
 // Octree_octreeIntersect (octree.h:41-109) for the thread-per-ray kernels (first-hit, preview, thread-per-pixel render):
 // the air steps run on the march layout, the leaf value / block test of a non-air leaf on the value-carrying layout.
 // hi.node is left at -1 (the first-hit kernel finds the treeData index of the hit voxel by one root descent).

@@ -33,6 +33,14 @@
 #ifndef CCU_Q_ROWS
 #define CCU_Q_ROWS 32
 #endif
+// q_shade: one march_begin + store site for both continuations of a path (0 = one per continuation)
+#ifndef CCU_SHADE_ONE_TAIL
+#define CCU_SHADE_ONE_TAIL 1
+#endif
+// straight-line march step (lean_step_flat) for the shallow layouts; 0 = the branching form (lean_probe)
+#ifndef CCU_FLAT_MARCH
+#define CCU_FLAT_MARCH 1
+#endif
 
 namespace ccu {
 
@@ -124,6 +132,7 @@ struct QueueParams {
     int bvh_warps;     // scheduler: only warps 0 .. bvh_warps-1 run the BVH stage
     int march_warps;   // scheduler: only warps 0 .. march_warps-1 run the MARCH stage
     int march_bias;    // scheduler: warps of sub-partitions 0..2 count MARCH columns +bias, warps of sub-partition 3 -bias
+    int sticky_min;    // scheduler: a warp repeats the one-shot stage it has just run while at least this many columns have work for it (33 = never)
     int shade_min;     // one-shot stages: a warp that got fewer slots than this puts them back and retries (q_pop_batch)
     int sky_texels;    // > 0: the launch reserved this many texels (4 bytes each) behind the other shared arrays for the sky table
     int *bvh_deep;     // CCU_BVH_PARK: global scratch for traversal-stack entries beyond Q_STACK, Q_DEEP words per slot and CTA
@@ -137,27 +146,51 @@ struct QueueParams {
 // the batches full; spreading the warps over different rows (measured) fragments the batches and is slower.
 // Masks are 32-bit words (shared-memory atomics are native on 32 bits): Q_MW words per stage and column, word w holds rows
 // 32 w .. 32 w + 31, at index (stage * Q_MW + w) * 32 + column.
+// Ordering between a slot's fields and its mask bit (both in shared memory, CTA scope): the push releases, a successful pop
+// acquires.  CCU_FENCE_MODE 3 (default): the atomics themselves carry the semantics (red.release.cta / atom.acquire.cta: on
+// shared memory the acquire side needs no fence instruction at all, the release side is MEMBAR.ALL.CTA + ATOMS);
+// 0: __threadfence_block (fence.sc.cta) on both sides; 1: fence.acq_rel.cta on both sides; 2: compiler barrier only
+// (experiment: relies on the in-order shared-memory pipeline, not on the memory model).
+#ifndef CCU_FENCE_MODE
+#define CCU_FENCE_MODE 3
+#endif
+__device__ __forceinline__ void q_fence() {
+#if CCU_FENCE_MODE == 0
+    __threadfence_block();
+#elif CCU_FENCE_MODE == 1
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+#else
+    asm volatile("" ::: "memory");
+#endif
+}
+__device__ __forceinline__ unsigned q_mask_and(unsigned *word, unsigned v) {
+#if CCU_FENCE_MODE == 3
+    unsigned old;
+    asm volatile("atom.acquire.cta.shared.and.b32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(word)), "r"(v) : "memory");
+    return old;
+#else
+    return atomicAnd(word, v);
+#endif
+}
+__device__ __forceinline__ void q_mask_or(unsigned *word, unsigned v) {
+#if CCU_FENCE_MODE == 3
+    asm volatile("red.release.cta.shared.or.b32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(word)), "r"(v) : "memory");
+#else
+    q_fence();
+    atomicOr(word, v);
+#endif
+}
 __device__ __forceinline__ int q_pop(unsigned *mask, int stage, int lane) {
 #pragma unroll
     for (int w = 0; w < Q_MW; w++) {
         unsigned *word = mask + (stage * Q_MW + w) * 32 + lane;
         unsigned m = *reinterpret_cast<volatile unsigned *>(word);
-#ifdef CCU_Q_FAIR
-        // experiment: the preferred row rotates with the SM clock (all warps of the SM agree on it, so rows still travel
-        // together), instead of row 0 always being served first
-        const unsigned rot = (unsigned)(clock() >> CCU_Q_FAIR) & 31u;
-#endif
         while (m) {
-#ifdef CCU_Q_FAIR
-            const unsigned mr = __funnelshift_r(m, m, rot);
-            const unsigned bit = 1u << ((__ffs((int)mr) - 1 + rot) & 31u);
-#else
             const unsigned bit = m & (0u - m);
-#endif
-            const unsigned old = atomicAnd(word, ~bit);
+            const unsigned old = q_mask_and(word, ~bit);
             QSTAT_LANE(14, 1);
             if (old & bit) {
-                __threadfence_block();
+                q_fence();
                 return w * 32 + __ffs((int)bit) - 1;
             }
             QSTAT_LANE(15, 1);
@@ -167,8 +200,7 @@ __device__ __forceinline__ int q_pop(unsigned *mask, int stage, int lane) {
     return -1;
 }
 __device__ __forceinline__ void q_push(unsigned *mask, int stage, int lane, int row) {
-    __threadfence_block();
-    atomicOr(mask + (stage * Q_MW + (Q_MW > 1 ? row >> 5 : 0)) * 32 + lane, 1u << (row & 31));
+    q_mask_or(mask + (stage * Q_MW + (Q_MW > 1 ? row >> 5 : 0)) * 32 + lane, 1u << (row & 31));
 }
 __device__ __forceinline__ bool q_has_work(const unsigned *mask, int stage, int lane) {
     unsigned any = 0;
@@ -249,7 +281,7 @@ __device__ __forceinline__ void q_stage_march(const DScene &s, const unsigned *_
     for (;;) {
         // Finished rays are handed over and idle lanes re-filled in batches: once refill_min lanes hold a finished
         // ray, or nothing is in flight.
-        if (busy - n_fly >= refill_min || n_fly == 0) {
+        {
             if (cur < 0 || done != 0) {
                 if (cur >= 0) {
                     F[QF_T * Q_SLOTS + cur] = __float_as_uint(r.t);
@@ -275,9 +307,16 @@ __device__ __forceinline__ void q_stage_march(const DScene &s, const unsigned *_
                 recheck--;
             }
         }
-        if (cur >= 0 && done == 0) done = lean_probe<LAY == 2, LAY == 0>(s, top, r);
-        n_fly = __popc(__ballot_sync(full, cur >= 0 && done == 0));
-        QSTAT(10, 1); QSTAT(11, n_fly);
+        // march until enough lanes hold a finished ray (or nothing is in flight): a tight inner loop with one backward branch
+        do {
+#if CCU_FLAT_MARCH
+            if (LAY != 2) done = lean_step_flat<LAY == 0>(s, top, r, cur >= 0 && done == 0, done);
+            else
+#endif
+            if (cur >= 0 && done == 0) done = lean_probe<LAY == 2, LAY == 0>(s, top, r);
+            n_fly = __popc(__ballot_sync(full, cur >= 0 && done == 0));
+            QSTAT(10, 1); QSTAT(11, n_fly);
+        } while (busy - n_fly < refill_min && n_fly != 0);
     }
     // park the rays still in flight, hand over the finished ones
     if (cur >= 0) {
@@ -298,6 +337,11 @@ __device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *
     bool bounce = false;
     float3 bounce_from = o;          // the shadow ray starts at the surface point
     float3 bounce_normal = f3(0, 0, 0);
+    // the ray this path continues with, if any: both continuations (shadow ray, bounce) share ONE march_begin + store site, so a
+    // batch that mixes them runs that code once
+    bool next_ray = false;
+    float3 next_o = o, next_d = d;
+    float next_limit = inff_();
     if (!ray_hit) {
         // kernel.h:26-31 with emittance 1 (path segment) or |d.n| (shadow ray)
         float3 throughput = f3(QFL(QF_THRX), QFL(QF_THRY), QFL(QF_THRZ));
@@ -329,9 +373,11 @@ __device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *
             QFL(QF_SHW) = fabsf(dot3(sd, hit.normal));
             QU(QF_META) = meta | QM_SHADOW;
             // the shadow ray starts at the surface point and inherits the surface hit's distance as its limit
-            March m;
-            const bool entered = march_begin(s, m, surf_point, sd, distance);
-            q_store_ray(F, mask, lane, row, m, entered);
+            next_ray = true;
+            next_o = surf_point; next_d = sd; next_limit = distance;
+#if !CCU_SHADE_ONE_TAIL
+            { March m; const bool entered = march_begin(s, m, next_o, next_d, next_limit); q_store_ray(F, mask, lane, row, m, entered); next_ray = false; }
+#endif
         } else {
             bounce = true;
             bounce_from = surf_point;
@@ -351,12 +397,16 @@ __device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *
         meta = (meta & ~(0xFFu << 16) & ~QM_SHADOW) | ((uint32_t)ray_depth << 16);
         QU(QF_META) = meta;
         if (ray_depth < s.max_depth) {
-            March m;
-            const bool entered = march_begin(s, m, no, nd, inff_());
-            q_store_ray(F, mask, lane, row, m, entered);
+            next_ray = true;
+            next_o = no; next_d = nd; next_limit = inff_();
         } else {
             q_push(mask, QS_END, lane, row);
         }
+    }
+    if (next_ray) {
+        March m;
+        const bool entered = march_begin(s, m, next_o, next_d, next_limit);
+        q_store_ray(F, mask, lane, row, m, entered);
     }
 }
 
@@ -927,9 +977,24 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
     const unsigned *top = LAY == 0 ? top_s : s.air_top;
 
     int held = 0;
+    int sticky = -1;   // the one-shot stage this warp has just run
     for (;;) {
         // the stage with the most columns that have work
         int best = -1, best_n = 0;
+        // A warp that has just run a one-shot stage runs it again while enough columns have work for it: the stage's code
+        // (several KB, far more than the L0 instruction cache) is then fetched once for several batches, and the scan over
+        // all stages is skipped.  BLOCK and EXIT are one piece of code (q_stage_resolve).
+        if (sticky >= 0) {
+            int n = __popc(__ballot_sync(full, q_has_work(mask, sticky, lane)));
+            int st2 = sticky;
+            if (sticky == QS_BLOCK || sticky == QS_EXIT) {
+                const int other = sticky == QS_BLOCK ? QS_EXIT : QS_BLOCK;
+                const int n2 = __popc(__ballot_sync(full, q_has_work(mask, other, lane)));
+                if (n2 > n) { n = n2; st2 = other; }
+            }
+            if (n >= qp.sticky_min) { best = st2; best_n = n; }
+        }
+        if (best < 0) {
 #pragma unroll
         for (int st = 0; st < NST; st++) {
             int n = __popc(__ballot_sync(full, q_has_work(mask, st, lane)));
@@ -941,6 +1006,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
             if (HAS_BVH && st == QS_BVH && (int)(threadIdx.x >> 5) >= qp.bvh_warps) n = 0;
             if (st == QS_MARCH && (int)(threadIdx.x >> 5) >= qp.march_warps) n = 0;
             if (n > best_n) { best_n = n; best = st; }
+        }
         }
         if (best < 0) {
             if (*reinterpret_cast<volatile int *>(live) == 0) break;
@@ -963,6 +1029,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
 #endif
             default: if (HAS_BVH) ran = q_stage_shade(s, F, mask, lane, min_lanes); break;
         }
+        sticky = (ran && best != QS_MARCH && best != QS_BVH) ? best : -1;
         if (ran) {
             held = 0;
         } else {

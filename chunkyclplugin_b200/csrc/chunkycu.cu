@@ -114,6 +114,10 @@ __global__ void __launch_bounds__(256, CCU_FH_MIN_BLOCKS) k_first_hit(const __gr
         int st = (valid && entered) ? 0 : 2;      // 0 marching, 1 at a non-air leaf, 2 left the octree without a hit, 3 hit
         for (;;) {
             while (__any_sync(full, st == 0)) {
+#if CCU_FLAT_MARCH
+                if (MODE != 2) st = lean_step_flat<false>(s, s.air_top, r, st == 0, st);
+                else
+#endif
                 if (st == 0) st = lean_probe<MODE == 2, false>(s, s.air_top, r);
             }
             if (st == 1) {
@@ -581,6 +585,7 @@ int ccu_ctx_create(int device_index, ccu_ctx **out) {
     if (const char *e = getenv("CCU_Q_LEAF_MIN")) c->q_leaf_min = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_Q_MARCH_BIAS")) c->q_march_bias = std::max(-32, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_Q_REFILL_MIN")) c->q_refill_min = std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("CCU_Q_STICKY")) c->q_sticky_min = std::max(1, std::min(33, atoi(e)));
     if (const char *e = getenv("CCU_Q_SHADE_MIN")) c->q_shade_min = std::max(0, std::min(32, atoi(e)));
     if (const char *e = getenv("CCU_YIELD_BELOW")) c->yield_below = std::max(0, std::min(33, atoi(e)));
     DeviceGuard g(device_index);
@@ -995,6 +1000,7 @@ static int render_passes_locked(ccu_ctx *c, const int32_t *seeds, int32_t n_pass
         qp.refill_min = c->q_refill_min;
         qp.march_bias = c->q_march_bias;
         qp.shade_min = c->q_shade_min;
+        qp.sticky_min = c->q_sticky_min > 0 ? c->q_sticky_min : (bvh ? 16 : 33);   // measured: -3 % with BVH stages, +5 % without
         qp.leaf_min = c->q_leaf_min;
         qp.bvh_warps = c->q_bvh_warps;
         qp.march_warps = bvh ? 64 : c->q_march_warps;   // with BVHs the service warps are the ones that do not walk

@@ -142,3 +142,12 @@ def test_libm_mode_statistically_equal():
     rel = np.sqrt(((a - b) ** 2).mean()) / np.sqrt((a ** 2).mean())
     assert rel < 0.02
     assert abs(a.mean() - b.mean()) / a.mean() < 1e-3
+
+
+def test_emittance_byte_quotient_equals_unorm_table():
+    """material.h:79 computes (float)((double)b / 255.0); the device reads the UNORM table entry (float)b / 255.0f instead.
+    Both are the same float for every byte value (the double quotient never lands on a rounding tie of the float grid)."""
+    b = np.arange(256)
+    via_double = (b.astype(np.float64) / 255.0).astype(np.float32)
+    via_float = b.astype(np.float32) / np.float32(255.0)
+    assert np.array_equal(via_double.view(np.uint32), via_float.view(np.uint32))
