@@ -38,6 +38,9 @@ __device__ __forceinline__ float dot3(float3 a, float3 b) { return __fmaf_rn(a.z
 __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
     return f3(__fmaf_rn(a.y, b.z, -(a.z * b.y)), __fmaf_rn(a.z, b.x, -(a.x * b.z)), __fmaf_rn(a.x, b.y, -(a.y * b.x)));
 }
+// One division site per role (scale, divide, second divide) instead of one per return path: the operations a given input goes
+// through are the same ones in the same order (v / inf for an infinite component; v / (m * r) normally; (v / r) / m when m * r
+// overflows), the quotients of the paths not taken are computed on the side and dropped.
 CCU_MATH_INLINE float3 normalize3(float3 v) {
     const float inf = __int_as_float(0x7f800000), qnan = __int_as_float(0x7fc00000);
     float ax = fabsf(v.x), ay = fabsf(v.y), az = fabsf(v.z);
@@ -45,12 +48,15 @@ CCU_MATH_INLINE float3 normalize3(float3 v) {
     float m = (ax < ay) ? ay : ax;
     m = (m < az) ? az : m;
     if (m == 0.0f) return f3(0, 0, 0);
-    if (m == inf) return f3(v.x / inf, v.y / inf, v.z / inf);
     float a = ax / m, b = ay / m, c = az / m;
     float r = sqrtf(__fmaf_rn(c, c, __fmaf_rn(a, a, b * b)));
     float len = m * r;
-    if (fabsf(len) != inf) return f3(v.x / len, v.y / len, v.z / len);
-    return f3((v.x / r) / m, (v.y / r) / m, (v.z / r) / m);
+    const bool by_inf = m == inf;                       // v / inf
+    const bool two_step = !by_inf && !(fabsf(len) != inf);   // (v / r) / m
+    const float d1 = by_inf ? inf : (two_step ? r : len);
+    float3 q = f3(v.x / d1, v.y / d1, v.z / d1);
+    if (two_step) q = f3(q.x / m, q.y / m, q.z / m);
+    return q;
 }
 // cvt.rzi.s32.f32: toward zero, saturating, NaN -> 0
 __device__ __forceinline__ int f2i(float f) { return __float2int_rz(f); }
@@ -80,22 +86,26 @@ __device__ __forceinline__ void dm_sincos(float x, float &s, float &c) { const f
 __device__ __forceinline__ float dm_cos(float x) { float s, c; dm_sincos(x, s, c); return c; }
 __device__ __forceinline__ float dm_sin(float x) { float s, c; dm_sincos(x, s, c); return s; }
 
+// One division, one polynomial: -(1 / t) == (-1) / t bit for bit (round-to-nearest is sign-symmetric), so both range
+// reductions are num / den with selected operands.
 __device__ __forceinline__ float dm_atan(float t) {
     float sign = 1.0f, y0 = 0.0f;
     if (t < 0.0f) { t = -t; sign = -1.0f; }
-    if (t > 2.414213562373095f) { y0 = 1.5707963267948966f; t = -(1.0f / t); }
-    else if (t > 0.4142135623730950f) { y0 = 0.7853981633974483f; t = (t - 1.0f) / (t + 1.0f); }
+    const bool big = t > 2.414213562373095f, mid = !big && t > 0.4142135623730950f;
+    if (big) y0 = 1.5707963267948966f;
+    if (mid) y0 = 0.7853981633974483f;
+    if (big || mid) t = (big ? -1.0f : t - 1.0f) / (big ? t : t + 1.0f);
     float z = t * t;
     float p = (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * t + t;
     return sign * (y0 + p);
 }
+// one dm_atan site: the quadrant offset is added afterwards (x > 0: none; x < 0: +pi for y >= 0, -pi for y < 0)
 CCU_MATH_INLINE float dm_atan2(float y, float x) {
     if (x != x || y != y) return nanf_();
-    if (x > 0.0f) return dm_atan(y / x);
-    if (x < 0.0f) return (y >= 0.0f) ? dm_atan(y / x) + 3.14159265358979f : dm_atan(y / x) - 3.14159265358979f;
-    if (y > 0.0f) return 1.5707963267948966f;
-    if (y < 0.0f) return -1.5707963267948966f;
-    return 0.0f;
+    if (x == 0.0f) return y > 0.0f ? 1.5707963267948966f : (y < 0.0f ? -1.5707963267948966f : 0.0f);
+    const float a = dm_atan(y / x);
+    if (x > 0.0f) return a;
+    return (y >= 0.0f) ? a + 3.14159265358979f : a - 3.14159265358979f;
 }
 CCU_MATH_INLINE float dm_asin(float x) {
     float a = fabsf(x);
@@ -107,11 +117,15 @@ CCU_MATH_INLINE float dm_asin(float x) {
     if (big) p = 1.5707963267948966f - (p + p);
     return x < 0.0f ? -p : p;
 }
+// one dm_asin site: 1 + x == 1 - |x| for x < -0.5 and 1 - x == 1 - |x| for x > 0.5 (a + b == a - (-b) exactly)
 __device__ __forceinline__ float dm_acos(float x) {
     if (fabsf(x) > 1.0f) return nanf_();
-    if (x < -0.5f) return 3.14159265358979f - 2.0f * dm_asin(sqrtf(0.5f * (1.0f + x)));
-    if (x > 0.5f) return 2.0f * dm_asin(sqrtf(0.5f * (1.0f - x)));
-    return 1.5707963267948966f - dm_asin(x);
+    const bool lo = x < -0.5f, hi = x > 0.5f;
+    const float arg = (lo || hi) ? sqrtf(0.5f * (1.0f - fabsf(x))) : x;
+    const float as = dm_asin(arg);
+    if (lo) return 3.14159265358979f - 2.0f * as;
+    if (hi) return 2.0f * as;
+    return 1.5707963267948966f - as;
 }
 
 // 256-bit read-only global load (LDG.E.256 on sm_100a): one instruction and one L1 tag lookup per lane for a 32-byte record half
