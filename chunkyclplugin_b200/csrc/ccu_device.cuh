@@ -48,7 +48,7 @@ struct DScene {
     const int *__restrict__ quad_models;
     const int *__restrict__ aabb_models;
     const int *__restrict__ mat_palette;
-    // 16-byte-vectorised palettes built at commit (use_recs): block_rec[2 * b] = {type, model ref, material flags, tint},
+    // 16-byte-vectorised palettes built at commit (always present): block_rec[2 * b] = {type, model ref, material flags, tint},
     // block_rec[2 * b + 1] = {texSize, texLocation / ARGB, emittance, spec} for palette position b (a full-cube block is ONE
     // 32-byte record: entry and material fused); mat_rec[2 * (ptr / 6)] the same six material words for everything else;
     // quad_rec / aabb_rec: {count, 0, 0, 0} followed by one 64-byte record per quad (15 words + pad) / box (13 words + pad),
@@ -57,7 +57,6 @@ struct DScene {
     const int4 *__restrict__ mat_rec;
     const int4 *__restrict__ quad_rec;
     const int4 *__restrict__ aabb_rec;
-    int use_recs;
     const int *__restrict__ world_bvh;
     const int *__restrict__ actor_bvh;
     const int *__restrict__ trigs;
@@ -240,7 +239,7 @@ __device__ __forceinline__ bool material_eval(const DScene &s, uint32_t flags, u
 // two 16-byte loads from the commit-time records, or the reference's own array for a pointer that is not on a record
 __device__ __forceinline__ bool material_sample(const DScene &s, int material, Surf &rec, float u, float v) {
     const int idx = material / 6;
-    if (s.use_recs && material >= 0 && idx * 6 == material) {
+    if (material >= 0 && idx * 6 == material) {
         const int4 a = __ldg(s.mat_rec + 2 * idx), b = __ldg(s.mat_rec + 2 * idx + 1);
         return material_eval(s, (uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, rec, u, v);
     }
@@ -401,36 +400,24 @@ static __device__ __noinline__ ModelHit intersect_model_block(const DScene &s, i
     float u = 0, v = 0;
     bool hit = false;
     float dist = inff_();
-    // model_ptr: offset into the reference's int arrays, or (use_recs) into the 16-byte record arrays in units of 16 bytes
+    // model_ptr: offset into the 16-byte record arrays built at commit, in units of 16 bytes
     int w[16];
     if (model_type == 2) {
-        const int boxes = s.use_recs ? __ldg(s.aabb_rec + model_ptr).x : __ldg(s.aabb_models + model_ptr);
+        const int boxes = __ldg(s.aabb_rec + model_ptr).x;
         for (int i = 0; i < boxes; i++) {
-            if (s.use_recs) {
-                const int4 *r = s.aabb_rec + model_ptr + 1 + 4 * i;
+            const int4 *r = s.aabb_rec + model_ptr + 1 + 4 * i;
 #pragma unroll
-                for (int k = 0; k < 4; k++) { const int4 t = __ldg(r + k); w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
-            } else {
-                const int *m = s.aabb_models + model_ptr + 1 + i * 13;
-#pragma unroll
-                for (int k = 0; k < 13; k++) w[k] = __ldg(m + k);
-            }
+            for (int k = 0; k < 4; k++) { const int4 t = __ldg(r + k); w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
             int material = 0;
             float t = textured_box(w, dist, norm_origin, direction, inv, normal, u, v, material);
             if (!is_nan(t) && material_sample(s, material, out.surf, u, v)) { out.surf.normal = normal; dist = t; hit = true; }
         }
     } else {
-        const int quads = s.use_recs ? __ldg(s.quad_rec + model_ptr).x : __ldg(s.quad_models + model_ptr);
+        const int quads = __ldg(s.quad_rec + model_ptr).x;
         for (int i = 0; i < quads; i++) {
-            if (s.use_recs) {
-                const int4 *r = s.quad_rec + model_ptr + 1 + 4 * i;
+            const int4 *r = s.quad_rec + model_ptr + 1 + 4 * i;
 #pragma unroll
-                for (int k = 0; k < 4; k++) { const int4 t = __ldg(r + k); w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
-            } else {
-                const int *q = s.quad_models + model_ptr + 1 + i * 15;
-#pragma unroll
-                for (int k = 0; k < 14; k++) w[k] = __ldg(q + k);
-            }
+            for (int k = 0; k < 4; k++) { const int4 t = __ldg(r + k); w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
             float t = quad_hit(w, dist, norm_origin, direction, normal, u, v);
             if (!is_nan(t) && material_sample(s, w[13], out.surf, u, v)) { out.surf.normal = normal; dist = t; hit = true; }
         }
@@ -446,14 +433,8 @@ __device__ __forceinline__ float intersect_block(const DScene &s, int block, int
                                                  float3 direction, float3 inv) {
     if (block == CCU_ANY_TYPE) return nanf_();
     if (block < 0 || block + 1 >= s.block_palette_len) return nanf_();   // out-of-palette leaf (undefined in the reference)
-    int model_type, model_ptr;
-    int4 r0 = make_int4(0, 0, 0, 0);
-    if (s.use_recs) {
-        r0 = __ldg(s.block_rec + 2 * block);
-        model_type = r0.x; model_ptr = r0.y;
-    } else {
-        model_type = __ldg(s.block_palette + block); model_ptr = __ldg(s.block_palette + block + 1);
-    }
+    const int4 r0 = __ldg(s.block_rec + 2 * block);
+    const int model_type = r0.x, model_ptr = r0.y;
     float3 norm_origin = (pos - direction * CCU_OFFSET) - f3((float)bx, (float)by, (float)bz);
     if (model_type == 1) {
         Box unit = {0, 1, 0, 1, 0, 1};
@@ -463,11 +444,9 @@ __device__ __forceinline__ float intersect_block(const DScene &s, int block, int
         float dist = box_full<false>(unit, norm_origin, pos, inv, normal, u, v);
         if (is_nan(dist)) return nanf_();
         Surf tmp;
-        if (s.use_recs) {
-            // the full cube's material travels with its palette entry
-            const int4 r1 = __ldg(s.block_rec + 2 * block + 1);
-            if (!material_eval(s, (uint32_t)r0.z, (uint32_t)r0.w, (uint32_t)r1.x, (uint32_t)r1.y, (uint32_t)r1.z, tmp, u, v)) return nanf_();
-        } else if (!material_sample(s, model_ptr, tmp, u, v)) return nanf_();
+        // the full cube's material travels with its palette entry
+        const int4 r1 = __ldg(s.block_rec + 2 * block + 1);
+        if (!material_eval(s, (uint32_t)r0.z, (uint32_t)r0.w, (uint32_t)r1.x, (uint32_t)r1.y, (uint32_t)r1.z, tmp, u, v)) return nanf_();
         surf.color = tmp.color;
         surf.emittance = tmp.emittance;
         surf.normal = normal;
@@ -793,25 +772,27 @@ __device__ __forceinline__ void camera_ray(const DScene &s, int gid, uint32_t &r
     }
 }
 
-// sky.h:68-93: direction towards the sun disc; x1, x2 are the two RNG draws (component-wise product u*v)
-__device__ __forceinline__ float3 sun_sample_direction(const DScene &s, float x1, float x2) {
+// sky.h:68-93: direction towards the sun disc; x1, x2 are the two RNG draws (component-wise product u*v).
+// Both direction samplers turn x2 into the same angle 2 pi x2; the *_sc forms take its sine / cosine so that a caller that needs
+// either one (the wavefront kernel's shading step) evaluates dm_sincos once for all its lanes.
+__device__ __forceinline__ float3 sun_sample_direction_sc(const DScene &s, float x1, float sn, float cs) {
     float cos_a = 1 - x1 + x1 * s.sun_radius_cos;
     float sin_a = sqrtf(1 - cos_a * cos_a);
-    float phi = 2 * CCU_PI_F * x2;
-    float sn, cs;
-    dm_sincos(phi, sn, cs);
     float3 u = s.su * (cs * sin_a);
     float3 v = s.sv * (sn * sin_a);
     float3 w = s.sw * cos_a;
     return normalize3((u * v) + w);
 }
+__device__ __forceinline__ float3 sun_sample_direction(const DScene &s, float x1, float x2) {
+    float phi = 2 * CCU_PI_F * x2;
+    float sn, cs;
+    dm_sincos(phi, sn, cs);
+    return sun_sample_direction_sc(s, x1, sn, cs);
+}
 
 // kernel.h:50-92: cosine-weighted diffuse bounce direction around normal n; x1, x2 are the two RNG draws
-__device__ __forceinline__ float3 diffuse_direction(float3 n, float x1, float x2) {
+__device__ __forceinline__ float3 diffuse_direction_sc(float3 n, float x1, float sn, float cs) {
     float r = sqrtf(x1);
-    float theta = 2 * CCU_PI_F * x2;
-    float sn, cs;
-    dm_sincos(theta, sn, cs);
     float tx = r * cs, ty = r * sn;
     float tz = sqrtf(1 - x1);
     float xx, xy, xz = 0;
@@ -825,6 +806,12 @@ __device__ __forceinline__ float3 diffuse_direction(float3 n, float x1, float x2
     float vy = uz * n.x - ux * n.z;
     float vz = ux * n.y - uy * n.x;
     return f3((ux * tx + vx * ty) + n.x * tz, (uy * tx + vy * ty) + n.y * tz, (uz * tx + vz * ty) + n.z * tz);
+}
+__device__ __forceinline__ float3 diffuse_direction(float3 n, float x1, float x2) {
+    float theta = 2 * CCU_PI_F * x2;
+    float sn, cs;
+    dm_sincos(theta, sn, cs);
+    return diffuse_direction_sc(n, x1, sn, cs);
 }
 
 }  // namespace ccu

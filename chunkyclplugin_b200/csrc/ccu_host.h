@@ -111,7 +111,6 @@ struct ccu_ctx {
     ccu_host::DevBuf<int> world_rec, actor_rec, tris2;          // BVH stage layout (ccu_queue.cuh)
     ccu_host::DevBuf<int> block_rec, mat_rec, quad_rec, aabb_rec;   // 16-byte-vectorised palettes (DScene::block_rec ...)
     std::vector<int> quad_host, aabb_host;
-    int use_recs = 0;
     int world_root = 0, actor_root = 0, use_bvh2 = 0, use_air = 0, air_deep = 0;
     int cell_level = 0, top_log2 = 0, use_wide = 0, air_cell_level = 4, air_top_log2 = 0;
     double commit_ms = 0;                                       // host time of the last ccu_scene_commit
@@ -156,7 +155,7 @@ struct ccu_ctx {
     int q_sticky_min = 0;      // 0 = default by kernel (CCU_Q_STICKY)
     int q_leaf_min = 12;
     int q_bvh_warps = CCU_BVH_PARK_DEFAULT_WARPS;
-    int q_march_warps = 22;
+    int q_march_warps = 18;
     int window_spp = 0;
     int closed_spp = 0;          // passes of the window closed by ccu_render_window_close, read-back in flight, not merged yet
     bool target_live = false;    // between ccu_render_begin and ccu_render_end

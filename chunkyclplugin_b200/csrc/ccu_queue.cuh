@@ -33,9 +33,8 @@
 #ifndef CCU_Q_ROWS
 #define CCU_Q_ROWS 32
 #endif
-// q_shade: one march_begin + store site for both continuations of a path (0 = one per continuation)
-#ifndef CCU_SHADE_ONE_TAIL
-#define CCU_SHADE_ONE_TAIL 1
+#ifndef CCU_MARCH_UNROLL
+#define CCU_MARCH_UNROLL 1
 #endif
 // straight-line march step (lean_step_flat) for the shallow layouts; 0 = the branching form (lean_probe)
 #ifndef CCU_FLAT_MARCH
@@ -310,8 +309,14 @@ __device__ __forceinline__ void q_stage_march(const DScene &s, const unsigned *_
         // march until enough lanes hold a finished ray (or nothing is in flight): a tight inner loop with one backward branch
         do {
 #if CCU_FLAT_MARCH
-            if (LAY != 2) done = lean_step_flat<LAY == 0>(s, top, r, cur >= 0 && done == 0, done);
-            else
+            if (LAY != 2) {
+                done = lean_step_flat<LAY == 0>(s, top, r, cur >= 0 && done == 0, done);
+#if CCU_MARCH_UNROLL > 1
+                // the lanes are counted every CCU_MARCH_UNROLL steps (a finished lane idles through the extra steps)
+#pragma unroll
+                for (int u = 1; u < CCU_MARCH_UNROLL; u++) done = lean_step_flat<LAY == 0>(s, top, r, cur >= 0 && done == 0, done);
+#endif
+            } else
 #endif
             if (cur >= 0 && done == 0) done = lean_probe<LAY == 2, LAY == 0>(s, top, r);
             n_fly = __popc(__ballot_sync(full, cur >= 0 && done == 0));
@@ -334,14 +339,12 @@ __device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *
     const int slot = row * 32 + lane;
     uint32_t meta = QU(QF_META) & ~QM_HIT;
     const bool shadow = (meta & QM_SHADOW) != 0;
-    bool bounce = false;
-    float3 bounce_from = o;          // the shadow ray starts at the surface point
-    float3 bounce_normal = f3(0, 0, 0);
-    // the ray this path continues with, if any: both continuations (shadow ray, bounce) share ONE march_begin + store site, so a
-    // batch that mixes them runs that code once
-    bool next_ray = false;
-    float3 next_o = o, next_d = d;
-    float next_limit = inff_();
+    // What the path continues with: the sun-sampling shadow ray (sky.h:68-93), the diffuse bounce (nextPath, kernel.h:46-98), or
+    // nothing (END).  Both continuations draw two random numbers, take the sine / cosine of 2 pi x2 and start a ray: that part is
+    // written ONCE below the case analysis, so a batch that mixes the cases runs it once.
+    bool sun = false, bounce = false;
+    float3 from = o;                 // the shadow ray starts at the surface point, so that is where its bounce starts
+    float3 normal = f3(0, 0, 0);     // surface normal for either continuation
     if (!ray_hit) {
         // kernel.h:26-31 with emittance 1 (path segment) or |d.n| (shadow ray)
         float3 throughput = f3(QFL(QF_THRX), QFL(QF_THRY), QFL(QF_THRZ));
@@ -357,49 +360,44 @@ __device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *
         // kernel.h:20-22 + applyRayColor kernel.h:33-44
         float3 throughput = f3(QFL(QF_THRX), QFL(QF_THRY), QFL(QF_THRZ));
         float3 color = f3(QFL(QF_COLX), QFL(QF_COLY), QFL(QF_COLZ));
-        float3 surf_point = o + d * (distance - CCU_OFFSET);
+        from = o + d * (distance - CCU_OFFSET);
         float3 col = f3(hit.color.x, hit.color.y, hit.color.z);
         throughput = throughput * col;
         color = color + (col * (hit.emittance * s.emitter_scale)) * throughput;
         QFL(QF_THRX) = throughput.x; QFL(QF_THRY) = throughput.y; QFL(QF_THRZ) = throughput.z;
         QFL(QF_COLX) = color.x; QFL(QF_COLY) = color.y; QFL(QF_COLZ) = color.z;
-        if (s.sun_flags & 1) {
-            QFL(QF_SNX) = hit.normal.x; QFL(QF_SNY) = hit.normal.y; QFL(QF_SNZ) = hit.normal.z;
-            uint32_t rng = QU(QF_RNG);
-            float x1 = rng_float(rng);
-            float x2 = rng_float(rng);
-            QU(QF_RNG) = rng;
-            float3 sd = sun_sample_direction(s, x1, x2);
-            QFL(QF_SHW) = fabsf(dot3(sd, hit.normal));
-            QU(QF_META) = meta | QM_SHADOW;
-            // the shadow ray starts at the surface point and inherits the surface hit's distance as its limit
-            next_ray = true;
-            next_o = surf_point; next_d = sd; next_limit = distance;
-#if !CCU_SHADE_ONE_TAIL
-            { March m; const bool entered = march_begin(s, m, next_o, next_d, next_limit); q_store_ray(F, mask, lane, row, m, entered); next_ray = false; }
-#endif
-        } else {
-            bounce = true;
-            bounce_from = surf_point;
-            bounce_normal = hit.normal;
-        }
+        normal = hit.normal;
+        if (s.sun_flags & 1) sun = true;
+        else bounce = true;
     }
-    if (bounce) {
-        // nextPath, kernel.h:46-98
-        if (shadow) bounce_normal = f3(QFL(QF_SNX), QFL(QF_SNY), QFL(QF_SNZ));
-        uint32_t rng = QU(QF_RNG);
-        float x1 = rng_float(rng);
-        float x2 = rng_float(rng);
-        QU(QF_RNG) = rng;
-        float3 nd = diffuse_direction(bounce_normal, x1, x2);
-        float3 no = bounce_from + nd * CCU_OFFSET;
+    if (!(sun || bounce)) return;
+    if (shadow) normal = f3(QFL(QF_SNX), QFL(QF_SNY), QFL(QF_SNZ));
+    uint32_t rng = QU(QF_RNG);
+    const float x1 = rng_float(rng);
+    const float x2 = rng_float(rng);
+    QU(QF_RNG) = rng;
+    float sn, cs;
+    dm_sincos(2 * CCU_PI_F * x2, sn, cs);
+    float3 next_o, next_d;
+    float next_limit;
+    bool next_ray = true;
+    if (sun) {
+        QFL(QF_SNX) = normal.x; QFL(QF_SNY) = normal.y; QFL(QF_SNZ) = normal.z;
+        next_d = sun_sample_direction_sc(s, x1, sn, cs);
+        QFL(QF_SHW) = fabsf(dot3(next_d, normal));
+        QU(QF_META) = meta | QM_SHADOW;
+        // the shadow ray starts at the surface point and inherits the surface hit's distance as its limit
+        next_o = from;
+        next_limit = distance;
+    } else {
+        next_d = diffuse_direction_sc(normal, x1, sn, cs);
+        next_o = from + next_d * CCU_OFFSET;
+        next_limit = inff_();
         const int ray_depth = (int)((meta >> 16) & 0xFF) + 1;
         meta = (meta & ~(0xFFu << 16) & ~QM_SHADOW) | ((uint32_t)ray_depth << 16);
         QU(QF_META) = meta;
-        if (ray_depth < s.max_depth) {
-            next_ray = true;
-            next_o = no; next_d = nd; next_limit = inff_();
-        } else {
+        if (!(ray_depth < s.max_depth)) {
+            next_ray = false;
             q_push(mask, QS_END, lane, row);
         }
     }
@@ -432,8 +430,8 @@ __device__ __forceinline__ bool q_stage_resolve(const DScene &s, uint32_t *F, un
     if (kind_block) {
         // the leaf under the ray (octree.h:81-88): value and level
         const Cell c = march_cell(m);
-        int level, node;
-        const int data = s.use_wide ? find_leaf_wide(s, c.bx, c.by, c.bz, level) : find_leaf(s, c.bx, c.by, c.bz, level, node);
+        int level;
+        const int data = find_leaf_wide(s, c.bx, c.by, c.bz, level);   // the kernel is only launched on the commit-time layouts
         if (!march_block(s, m, data, level, hit, hit_t)) {
             QFL(QF_T) = m.t; QI(QF_STEPS) = m.steps;
             q_push(mask, QS_MARCH, lane, row);

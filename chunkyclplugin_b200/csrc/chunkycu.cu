@@ -331,7 +331,6 @@ void fill_scene(ccu_ctx *c) {
     s.mat_rec = reinterpret_cast<const int4 *>(c->mat_rec.p);
     s.quad_rec = reinterpret_cast<const int4 *>(c->quad_rec.p);
     s.aabb_rec = reinterpret_cast<const int4 *>(c->aabb_rec.p);
-    s.use_recs = c->use_recs;
     s.world_bvh = c->world_bvh.p;
     s.actor_bvh = c->actor_bvh.p;
     s.trigs = c->trigs.p;
@@ -516,7 +515,6 @@ int replicate_scene(ccu_ctx *src, ccu_ctx *dst) {
     dst->actor_host = src->actor_host.size() >= 7 ? std::vector<int>(src->actor_host.begin(), src->actor_host.begin() + 7) : src->actor_host;
     dst->tree_host.clear(); dst->trigs_host.clear(); dst->block_host.clear(); dst->mat_host.clear();
     dst->world_root = src->world_root; dst->actor_root = src->actor_root; dst->use_bvh2 = src->use_bvh2; dst->use_air = src->use_air;
-    dst->use_recs = src->use_recs;
     dst->air_deep = src->air_deep; dst->cell_level = src->cell_level; dst->top_log2 = src->top_log2; dst->use_wide = src->use_wide;
     dst->air_cell_level = src->air_cell_level; dst->air_top_log2 = src->air_top_log2;
     dst->atlas_w = src->atlas_w; dst->atlas_h = src->atlas_h; dst->atlas_layers = src->atlas_layers;
@@ -806,7 +804,6 @@ int ccu_scene_commit(ccu_ctx *c) {
     // 16-byte-vectorised block / material / model palettes
     {
         PaletteRecs pr = build_palette_recs(c->block_host, c->mat_host, c->quad_host.data(), c->quad_host.size(), c->aabb_host.data(), c->aabb_host.size());
-        c->use_recs = getenv("CCU_NO_RECS") == nullptr ? 1 : 0;
         CU(c->block_rec.upload(pr.block.data(), pr.block.size(), c->stream));
         CU(c->mat_rec.upload(pr.mat.data(), pr.mat.size(), c->stream));
         CU(c->quad_rec.upload(pr.quad.data(), pr.quad.size(), c->stream));
