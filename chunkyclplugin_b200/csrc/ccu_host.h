@@ -29,12 +29,15 @@ const char *last_error();
 
 template <class T>
 struct DevBuf {
+    // never smaller than one 64-byte record: the straight-line kernels read element 0 of an empty array on lanes that have no
+    // work (the value is dropped)
+    static constexpr size_t MIN_ELEMS = 64 / sizeof(T) > 4 ? 64 / sizeof(T) : 4;
     T *p = nullptr;
     size_t n = 0;
     cudaError_t alloc(size_t count) {
         release();
         n = count;
-        const size_t a = std::max<size_t>(count, 4);   // zero-length arrays become a zero word (ClIntBuffer.java:15-18)
+        const size_t a = std::max<size_t>(count, MIN_ELEMS);   // zero-length arrays become zero words (ClIntBuffer.java:15-18)
         cudaError_t e = cudaMalloc(&p, a * sizeof(T));
         if (e != cudaSuccess) { p = nullptr; n = 0; }
         return e;
@@ -42,7 +45,7 @@ struct DevBuf {
     cudaError_t upload(const T *host, size_t count, cudaStream_t st) {
         cudaError_t e = alloc(count);
         if (e != cudaSuccess) return e;
-        e = cudaMemsetAsync(p, 0, std::max<size_t>(count, 4) * sizeof(T), st);
+        e = cudaMemsetAsync(p, 0, std::max<size_t>(count, MIN_ELEMS) * sizeof(T), st);
         if (e != cudaSuccess) return e;
         if (count) e = cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) return e;
@@ -53,7 +56,7 @@ struct DevBuf {
         p = nullptr;
         n = 0;
     }
-    size_t bytes() const { return p ? std::max<size_t>(n, 4) * sizeof(T) : 0; }
+    size_t bytes() const { return p ? std::max<size_t>(n, MIN_ELEMS) * sizeof(T) : 0; }
 };
 
 constexpr int SEED_SLOTS = 4, SEED_SLOT_INTS = 32768;   // one launch covers at most 32768 passes (16-bit pass index in the wavefront kernel)

@@ -33,6 +33,10 @@
 #ifndef CCU_Q_ROWS
 #define CCU_Q_ROWS 32
 #endif
+// shadow rays skip what cannot change their answer (BVHs after an octree hit, the walk after the first accepted triangle)
+#ifndef CCU_SHADOW_SHORTCUT
+#define CCU_SHADOW_SHORTCUT 1
+#endif
 #ifndef CCU_MARCH_UNROLL
 #define CCU_MARCH_UNROLL 1
 #endif
@@ -104,7 +108,7 @@ __host__ __device__ constexpr int q_smem_bytes(bool bvh, bool tops) { return (q_
 #ifdef CCU_Q_STATS
 // debug counters (build with -DCCU_Q_STATS): [2*st] = executions of stage st, [2*st+1] = lanes that had a slot;
 // [10] march iterations, [11] lanes in flight summed over iterations, [12] scheduler rounds that found no work,
-// [13] march yields, [14] pop attempts, [15] pop retries
+// [13] march yields, [14] pop attempts, [15] pop retries, [24] march refills, [25] BVH refills
 __device__ unsigned long long g_qstats[32];   // [16] BVH stage entries, [18] BVH steps, [19] walking lanes, [20] leaf turns, [21] leaf lanes, [22] SHADE runs, [23] lanes
 #define QSTAT(i, v) do { const unsigned long long v_ = (unsigned long long)(v); if ((threadIdx.x & 31) == 0) atomicAdd(&g_qstats[i], v_); } while (0)
 #define QSTAT_LANE(i, v) atomicAdd(&g_qstats[i], (unsigned long long)(v))
@@ -293,6 +297,7 @@ __device__ __forceinline__ void q_stage_march(const DScene &s, const unsigned *_
                 if (cur >= 0) q_load_lean(F, cur, r);
             }
             busy = __popc(__ballot_sync(full, cur >= 0));
+            QSTAT(24, 1);
             if (busy == 0) return;
             if (busy < yield_below) {
                 // few busy lanes: switch when another stage has more lanes' worth of work than this warp is using
@@ -450,6 +455,14 @@ __device__ __forceinline__ bool q_stage_resolve(const DScene &s, uint32_t *F, un
         }
         const uint32_t meta = QU(QF_META);
         QU(QF_META) = ray_hit ? (meta | QM_HIT) : (meta & ~QM_HIT);
+#if CCU_BVH_PARK && CCU_SHADOW_SHORTCUT
+        // A shadow ray only asks WHETHER something lies between the surface and the sun (rayTracer.cl:101-106 uses nothing else
+        // of its record): once the octree has answered yes, the BVHs - which can only find a closer hit - cannot change that.
+        if (ray_hit && (meta & QM_SHADOW)) {
+            q_push(mask, QS_SHADE, lane, row);
+            return true;
+        }
+#endif
 #if CCU_BVH_PARK
         // kernel.h:17-18: the world BVH first, then the actor BVH (the kernel is only launched when at least one is not empty)
         int ref, phase;
@@ -558,44 +571,47 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
     int ref = 0, sp = 0, phase = 2;
     int busy = 0, n_fly = 0, recheck = 0;
     for (;;) {
-        if (busy - n_fly >= refill_min || n_fly == 0) {
-            if (cur < 0 || phase >= 2 || ref < 0) {
-                if (cur >= 0) {
-                    F[QF_BREF * Q_SLOTS + cur] = (uint32_t)ref;
-                    F[QF_BSP * Q_SLOTS + cur] = (uint32_t)(sp | (phase << 8));
-                    q_push(mask, phase >= 2 ? QS_SHADE : QS_LEAF, cur & 31, cur >> 5);
-                }
-                const int row = q_pop(mask, QS_BVH, lane);
-                cur = row < 0 ? -1 : row * 32 + lane;
-                phase = 2; ref = 0;
-                if (cur >= 0) {
-                    const int slot = cur;
-                    o = f3(QFL(QF_OX), QFL(QF_OY), QFL(QF_OZ));
-                    inv = f3(QFL(QF_IX), QFL(QF_IY), QFL(QF_IZ));      // 1 / d, the same quotients bvh.h:40 computes
-                    dist = QFL(QF_HDIST);
-                    ref = QI(QF_BREF);
-                    const int bsp = QI(QF_BSP);
-                    sp = bsp & 0xFF;
-                    phase = bsp >> 8;
-                }
+        // hand-over / refill (see q_stage_march)
+        if (cur < 0 || phase >= 2 || ref < 0) {
+            if (cur >= 0) {
+                F[QF_BREF * Q_SLOTS + cur] = (uint32_t)ref;
+                F[QF_BSP * Q_SLOTS + cur] = (uint32_t)(sp | (phase << 8));
+                q_push(mask, phase >= 2 ? QS_SHADE : QS_LEAF, cur & 31, cur >> 5);
             }
-            busy = __popc(__ballot_sync(full, cur >= 0));
-            if (busy == 0) return;
-            if (busy < yield_below) {
-                if (recheck == 0) {
-                    int best = 0;
-#pragma unroll
-                    for (int st = 0; st < NST; st++)
-                        if (st != QS_BVH) best = max(best, __popc(__ballot_sync(full, q_has_work(mask, st, lane))));
-                    if (best > busy) break;
-                    recheck = 4;
-                }
-                recheck--;
+            const int row = q_pop(mask, QS_BVH, lane);
+            cur = row < 0 ? -1 : row * 32 + lane;
+            phase = 2; ref = 0;
+            if (cur >= 0) {
+                const int slot = cur;
+                o = f3(QFL(QF_OX), QFL(QF_OY), QFL(QF_OZ));
+                inv = f3(QFL(QF_IX), QFL(QF_IY), QFL(QF_IZ));      // 1 / d, the same quotients bvh.h:40 computes
+                dist = QFL(QF_HDIST);
+                ref = QI(QF_BREF);
+                const int bsp = QI(QF_BSP);
+                sp = bsp & 0xFF;
+                phase = bsp >> 8;
             }
         }
-        if (cur >= 0 && phase < 2 && ref >= 0) {
+        busy = __popc(__ballot_sync(full, cur >= 0));
+        QSTAT(25, 1);
+        if (busy == 0) return;
+        if (busy < yield_below) {
+            if (recheck == 0) {
+                int best = 0;
+#pragma unroll
+                for (int st = 0; st < NST; st++)
+                    if (st != QS_BVH) best = max(best, __popc(__ballot_sync(full, q_has_work(mask, st, lane))));
+                if (best > busy) break;
+                recheck = 4;
+            }
+            recheck--;
+        }
+        // inner-node steps until enough lanes wait at a leaf / have finished (or none is walking): a tight loop with one backward
+        // branch; lanes that are not at an inner node pass through on dummy values (record 0 of the world BVH) and commit nothing
+        do {
+            const bool on = cur >= 0 && phase < 2 && ref >= 0;
             // inner node: both children's boxes (bvh.h:73-108)
-            const int4 *r = (phase == 0 ? s.world_rec : s.actor_rec) + (size_t)ref * 4;
+            const int4 *r = ((on && phase != 0) ? s.actor_rec : s.world_rec) + (size_t)(on ? ref : 0) * 4;
             const Int8 lo = ldg256(r), hi = ldg256(r + 2);
             const Box b1 = {i2f(lo.v[0]), i2f(lo.v[1]), i2f(lo.v[2]), i2f(lo.v[3]), i2f(lo.v[4]), i2f(lo.v[5])};
             const Box b2 = {i2f(lo.v[6]), i2f(lo.v[7]), i2f(hi.v[0]), i2f(hi.v[1]), i2f(hi.v[2]), i2f(hi.v[3])};
@@ -606,17 +622,21 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
             const int left = hi.v[4], right = hi.v[5];
             // bvh.h:93-108: both missed -> next pending node; one hit -> that child; both hit -> the nearer one, the other is
             // left pending.  Written with selects so that only the stack accesses themselves are divergent.
-            const bool both = !miss1 && !miss2, none = miss1 && miss2;
+            const bool both = on && !miss1 && !miss2, none = on && miss1 && miss2;
             const bool go_left = both ? t1 < t2 : !miss1;
             bvh_stack_push(stk, deep, cur, sp, go_left ? right : left, both);
             sp += both ? 1 : 0;
-            ref = go_left ? left : right;
+            int nref = go_left ? left : right;
             const bool pop = none && sp > 0;
             sp -= pop ? 1 : 0;
-            ref = bvh_stack_pop(stk, deep, cur, sp, pop, ref);
-            if (none && !pop) bvh_phase_done(s, ref, phase);
-        }
-        n_fly = __popc(__ballot_sync(full, cur >= 0 && phase < 2 && ref >= 0));
+            nref = bvh_stack_pop(stk, deep, cur, sp, pop, nref);
+            int nphase = phase;
+            if (none && !pop) bvh_phase_done(s, nref, nphase);
+            ref = on ? nref : ref;
+            phase = on ? nphase : phase;
+            n_fly = __popc(__ballot_sync(full, cur >= 0 && phase < 2 && ref >= 0));
+            QSTAT(18, 1); QSTAT(19, n_fly);
+        } while (busy - n_fly < refill_min && n_fly != 0);
     }
     // park the walks still at inner nodes, hand over the others
     if (cur >= 0) {
@@ -646,6 +666,10 @@ __device__ __forceinline__ bool q_stage_leaf(const DScene &s, uint32_t *F, unsig
     bool any = false;
     const int *blk = s.tris2 + (size_t)(-(ref + 1)) * 8;
     const int num = __ldg(blk);
+    const uint32_t meta = QU(QF_META);
+    // a shadow ray is answered by its first accepted triangle (see q_stage_resolve): the rest of the walk could only find a
+    // closer one
+    const bool first_hit_ends = CCU_SHADOW_SHORTCUT && (meta & QM_SHADOW) != 0;
     for (int i = 0; i < num; i++) {
         float3 normal;
         float u, v;
@@ -655,6 +679,7 @@ __device__ __forceinline__ bool q_stage_leaf(const DScene &s, uint32_t *F, unsig
             hit.normal = normal;
             dist = t;
             any = true;
+            if (first_hit_ends) break;
         }
     }
     if (any) {
@@ -663,9 +688,10 @@ __device__ __forceinline__ bool q_stage_leaf(const DScene &s, uint32_t *F, unsig
         QFL(QF_HEM) = hit.emittance;
         QFL(QF_HNX) = hit.normal.x; QFL(QF_HNY) = hit.normal.y; QFL(QF_HNZ) = hit.normal.z;
         QFL(QF_HCX) = hit.color.x; QFL(QF_HCY) = hit.color.y; QFL(QF_HCZ) = hit.color.z;
-        QU(QF_META) |= QM_HIT;
+        QU(QF_META) = meta | QM_HIT;
     }
-    if (sp == 0) bvh_phase_done(s, ref, phase);
+    if (any && first_hit_ends) { phase = 2; ref = 0; }
+    else if (sp == 0) bvh_phase_done(s, ref, phase);
     else { sp--; ref = bvh_stack_pop(stk, deep, slot, sp, true, ref); }
     QI(QF_BREF) = ref;
     QI(QF_BSP) = sp | (phase << 8);

@@ -1042,6 +1042,7 @@ static int render_passes_locked(ccu_ctx *c, const int32_t *seeds, int32_t n_pass
                     st[10] ? (double)st[11] / st[10] : 0.0, st[13], st[12], st[14], st[15]);
             fprintf(stderr, "[qstats] bvh stages %llu, steps %llu x %.1f walking lanes, leaf turns %llu x %.1f lanes, shade %llu x %.1f lanes\n", st[16], st[18],
                     st[18] ? (double)st[19] / st[18] : 0.0, st[20], st[20] ? (double)st[21] / st[20] : 0.0, st[22], st[22] ? (double)st[23] / st[22] : 0.0);
+            fprintf(stderr, "[qstats] march refills %llu, bvh refills %llu\n", st[24], st[25]);
             unsigned long long z[32] = {0};
             cudaMemcpyToSymbol(g_qstats, z, sizeof z);
         }
