@@ -37,6 +37,12 @@
 #ifndef CCU_SHADOW_SHORTCUT
 #define CCU_SHADOW_SHORTCUT 1
 #endif
+// BVH stage prefetches (bit mask): 1 = the pending (far) child when it is pushed and a leaf block when a walk arrives at it;
+// 2 = both children as soon as their parent's record is read; 4 = inside a leaf, the rest of the current triangle and the head
+// of the next one
+#ifndef CCU_BVH_PREFETCH
+#define CCU_BVH_PREFETCH 0
+#endif
 #ifndef CCU_MARCH_UNROLL
 #define CCU_MARCH_UNROLL 1
 #endif
@@ -559,6 +565,12 @@ __device__ __forceinline__ int bvh_stack_pop(int *stk, int *deep, int slot, int 
     return v;
 }
 
+// L1 prefetch of the record of inner node `ref` (64 bytes) or of the head of leaf block `ref` (count word + first triangle)
+__device__ __forceinline__ void bvh_prefetch(const DScene &s, const int4 *rec, int ref) {
+    const char *a = ref >= 0 ? reinterpret_cast<const char *>(rec + (size_t)ref * 4) : reinterpret_cast<const char *>(s.tris2 + (size_t)(-(ref + 1)) * 8);
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(a));
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(a + 32));
+}
 // QS_BVH: inner-node steps (bvh.h:73-108) for walks that sit at inner nodes.  Organised like MARCH: a lane keeps its walk in
 // registers while it steps from inner node to inner node; a walk that reaches a leaf or finishes is handed over (QS_LEAF /
 // QS_SHADE) and the lane takes the next waiting walk, in batches; a warp with too few walks parks them and switches stage.
@@ -611,7 +623,8 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
         do {
             const bool on = cur >= 0 && phase < 2 && ref >= 0;
             // inner node: both children's boxes (bvh.h:73-108)
-            const int4 *r = ((on && phase != 0) ? s.actor_rec : s.world_rec) + (size_t)(on ? ref : 0) * 4;
+            const int4 *rbase = (on && phase != 0) ? s.actor_rec : s.world_rec;
+            const int4 *r = rbase + (size_t)(on ? ref : 0) * 4;
             const Int8 lo = ldg256(r), hi = ldg256(r + 2);
             const Box b1 = {i2f(lo.v[0]), i2f(lo.v[1]), i2f(lo.v[2]), i2f(lo.v[3]), i2f(lo.v[4]), i2f(lo.v[5])};
             const Box b2 = {i2f(lo.v[6]), i2f(lo.v[7]), i2f(hi.v[0]), i2f(hi.v[1]), i2f(hi.v[2]), i2f(hi.v[3])};
@@ -620,11 +633,16 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
             const bool miss1 = is_nan(t1) || t1 > dist;
             const bool miss2 = is_nan(t2) || t2 > dist;
             const int left = hi.v[4], right = hi.v[5];
+#if CCU_BVH_PREFETCH & 2
+            // both children's records (or leaf blocks) towards L1 while the box tests run
+            if (on) { bvh_prefetch(s, rbase, left); bvh_prefetch(s, rbase, right); }
+#endif
             // bvh.h:93-108: both missed -> next pending node; one hit -> that child; both hit -> the nearer one, the other is
             // left pending.  Written with selects so that only the stack accesses themselves are divergent.
             const bool both = on && !miss1 && !miss2, none = on && miss1 && miss2;
             const bool go_left = both ? t1 < t2 : !miss1;
-            bvh_stack_push(stk, deep, cur, sp, go_left ? right : left, both);
+            const int far = go_left ? right : left;
+            bvh_stack_push(stk, deep, cur, sp, far, both);
             sp += both ? 1 : 0;
             int nref = go_left ? left : right;
             const bool pop = none && sp > 0;
@@ -632,6 +650,11 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
             nref = bvh_stack_pop(stk, deep, cur, sp, pop, nref);
             int nphase = phase;
             if (none && !pop) bvh_phase_done(s, nref, nphase);
+#if CCU_BVH_PREFETCH & 1
+            // the node left pending will be popped later, a leaf is visited after a trip through the LEAF queue: start both loads now
+            if (both) bvh_prefetch(s, rbase, far);
+            if (on && nphase < 2 && nref < 0) bvh_prefetch(s, rbase, nref);
+#endif
             ref = on ? nref : ref;
             phase = on ? nphase : phase;
             n_fly = __popc(__ballot_sync(full, cur >= 0 && phase < 2 && ref >= 0));
@@ -674,6 +697,11 @@ __device__ __forceinline__ bool q_stage_leaf(const DScene &s, uint32_t *F, unsig
         float3 normal;
         float u, v;
         int material;
+#if CCU_BVH_PREFETCH & 4
+        // the second 32 bytes of this triangle (read after the determinant test) and the first 32 of the next one
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(blk + 8 + 24 * i + 8));
+        if (i + 1 < num) asm volatile("prefetch.global.L1 [%0];" :: "l"(blk + 8 + 24 * i + 24));
+#endif
         const float t = triangle_hit_aligned(blk + 8 + 24 * i, dist, o, d, normal, u, v, material);
         if (!is_nan(t) && material_sample(s, material, hit, u, v)) {
             hit.normal = normal;

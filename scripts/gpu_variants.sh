@@ -22,5 +22,5 @@ for spec in "$@"; do
   lib=/tmp/ccu_variants/$name.so
   [ -z "$flags" ] && lib=/tmp/ccu_variants/base.so
   [ -f "$lib" ] || continue
-  env $envs CHUNKYCU_LIB=$lib timeout 300 python scripts/qbench.py --tag "$name" ${qargs:---workloads config1} 2>&1 | grep -v "^$" | tee -a gpurun_out/variants.jsonl
+  env $envs CHUNKYCU_LIB=$lib timeout 120 python scripts/qbench.py --tag "$name" ${qargs:---workloads config1} 2>&1 | grep -v "^$" | tee -a gpurun_out/variants.jsonl
 done
