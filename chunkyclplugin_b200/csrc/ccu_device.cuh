@@ -139,6 +139,16 @@ __device__ __forceinline__ void stage_tables(const DScene &s, const uchar4 *sky_
     if (threadIdx.x == 0) t.sky = sky_smem ? sky_smem : s.sky;
     __syncthreads();
 }
+// The same without a block barrier, for the short thread-per-ray kernels: EVERY warp writes the whole table (all warps write the
+// same values, so it does not matter whose store lands last) and only waits for its own lanes.
+__device__ __forceinline__ void stage_tables_per_warp(const DScene &s) {
+    SmemTables &t = smem_tables();
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.unorm[i * 32 + lane] = __ldg(s.unorm + i * 32 + lane);
+    if (lane == 0) t.sky = s.sky;
+    __syncwarp();
+}
 // RGBA8 UNORM -> float: byte / 255.0f, read from a 256-entry table holding exactly those IEEE quotients
 // (built once on the device by k_unorm_table), which replaces four divisions per texel by four shared-memory loads.
 __device__ __forceinline__ float4 unorm8(const DScene &s, uchar4 t) {
@@ -736,14 +746,13 @@ __device__ __forceinline__ float3 sky_radiance(const DScene &s, float3 d) {
 }
 
 // camera.h:8-32 + rayTracer.cl:55-91 (NORMALIZE = preview variant, rayTracer.cl:186)
+// (px, py): the pixel's column / row, gid = py * width + px (callers that already know them spare the division)
 template <bool NORMALIZE>
-__device__ __forceinline__ void camera_ray(const DScene &s, int gid, uint32_t &rng, float3 &origin, float3 &direction) {
+__device__ __forceinline__ void camera_ray_xy(const DScene &s, int gid, int px, int py, uint32_t &rng, float3 &origin, float3 &direction) {
     if (s.projector_type != -1) {
         // half_width = (float)(W / (2.0 * H)), inv_height = (float)(1.0 / H): the double expressions of
         // rayTracer.cl:66-67, evaluated once on the host (IEEE doubles, identical on any machine)
         const float half_width = s.half_width, inv_height = s.inv_height;
-        int py = gid / s.width;
-        int px = gid - py * s.width;
         float x = -half_width + ((float)px + rng_float(rng)) * inv_height;
         float y = (float)(-0.5 + (double)(((float)py + rng_float(rng)) * inv_height));
         float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
@@ -770,6 +779,12 @@ __device__ __forceinline__ void camera_ray(const DScene &s, int gid, uint32_t &r
         origin = f3(__ldg(r), __ldg(r + 1), __ldg(r + 2));
         direction = f3(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
     }
+}
+
+template <bool NORMALIZE>
+__device__ __forceinline__ void camera_ray(const DScene &s, int gid, uint32_t &rng, float3 &origin, float3 &direction) {
+    const int py = gid / s.width;
+    camera_ray_xy<NORMALIZE>(s, gid, gid - py * s.width, py, rng, origin, direction);
 }
 
 // sky.h:68-93: direction towards the sun disc; x1, x2 are the two RNG draws (component-wise product u*v).

@@ -866,29 +866,41 @@ constexpr unsigned Q_CHUNK = Q_TILE_W * Q_TILE_H;
 // PATCH: inside full 32x32 tiles, 32 consecutive k cover an 8x4 pixel patch instead of a 32x1 strip (thread-per-ray kernels:
 // a warp's rays then form a compact bundle).
 template <bool PATCH = false>
-__device__ __forceinline__ int tile_order_pixel(unsigned k, int W, int H) {
+__device__ __forceinline__ void tile_order_xy(unsigned k, int W, int H, unsigned &px, unsigned &py) {
     const unsigned band_px = (unsigned)W * Q_TILE_H;
     const unsigned band = k / band_px;
     const unsigned kb = k - band * band_px;
     const unsigned bh = min((unsigned)Q_TILE_H, (unsigned)H - band * Q_TILE_H);     // rows in this band
-    const unsigned tile_px = Q_TILE_W * bh;
     const unsigned full_tiles = (unsigned)W / Q_TILE_W;
-    unsigned tile = kb / tile_px;
-    unsigned tw = Q_TILE_W;
-    unsigned in = kb - tile * tile_px;
-    if (tile >= full_tiles) {            // the narrower remainder tile at the right edge
-        tile = full_tiles;
-        tw = (unsigned)W - full_tiles * Q_TILE_W;
-        in = kb - full_tiles * tile_px;
+    unsigned tile, tw = Q_TILE_W, in, iy, ix;
+    if (bh == Q_TILE_H && kb < full_tiles * Q_CHUNK) {
+        // a full 32x32 tile (all but the last band / last column of tiles): shifts only
+        tile = kb / Q_CHUNK;
+        in = kb % Q_CHUNK;
+        iy = in / Q_TILE_W; ix = in % Q_TILE_W;
+    } else {
+        const unsigned tile_px = Q_TILE_W * bh;
+        tile = kb / tile_px;
+        in = kb - tile * tile_px;
+        if (tile >= full_tiles) {            // the narrower remainder tile at the right edge
+            tile = full_tiles;
+            tw = (unsigned)W - full_tiles * Q_TILE_W;
+            in = kb - full_tiles * tile_px;
+        }
+        iy = in / tw; ix = in % tw;
     }
-    unsigned iy = in / tw, ix = in % tw;
     if (PATCH && tw == Q_TILE_W && bh == Q_TILE_H) {
         // in = [y4 y3 y2 | x4 x3 | y1 y0 | x2 x1 x0]
         ix = (in & 7u) | (((in >> 5) & 3u) << 3);
         iy = ((in >> 3) & 3u) | ((in >> 7) << 2);
     }
-    const unsigned py = band * Q_TILE_H + iy;
-    const unsigned px = tile * Q_TILE_W + ix;
+    py = band * Q_TILE_H + iy;
+    px = tile * Q_TILE_W + ix;
+}
+template <bool PATCH = false>
+__device__ __forceinline__ int tile_order_pixel(unsigned k, int W, int H) {
+    unsigned px, py;
+    tile_order_xy<PATCH>(k, W, H, px, py);
     return (int)(py * (unsigned)W + px);
 }
 

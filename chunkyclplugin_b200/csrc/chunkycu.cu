@@ -82,88 +82,118 @@ __device__ __forceinline__ int face_of(float3 n) {
 // together (the block test is ~3x the instructions of a march step; run per lane as each ray arrives it executed at 6 of 32
 // lanes), and repeats for the lanes whose block test missed.  The treeData index of the hit leaf (reference numbering,
 // ClSceneLoader.java:56-59) is found by one root descent for the hit voxel only.  HAS_BVH = false compiles the entity BVHs out.
+#ifndef CCU_FH_WARP_SKIP
+#define CCU_FH_WARP_SKIP 0
+#endif
 #ifndef CCU_FH_MIN_BLOCKS
 #define CCU_FH_MIN_BLOCKS 4
 #endif
+struct FirstHitOut { int *block, *face, *node, *kind; float *t, *normal, *color; };
+__device__ __forceinline__ void first_hit_store(const FirstHitOut &out, int gid, bool hit, int material, float3 n, int node, int kind, float t, float4 color) {
+    if (out.block) out.block[gid] = hit ? material : 0;
+    if (out.face) out.face[gid] = hit ? face_of(n) : 6;
+    if (out.node) out.node[gid] = hit ? node : -1;
+    if (out.kind) out.kind[gid] = hit ? kind : 0;
+    if (out.t) out.t[gid] = hit ? t : inff_();
+    if (out.normal) {
+        out.normal[gid * 3 + 0] = hit ? n.x : 0.0f;
+        out.normal[gid * 3 + 1] = hit ? n.y : 0.0f;
+        out.normal[gid * 3 + 2] = hit ? n.z : 0.0f;
+    }
+    if (out.color) reinterpret_cast<float4 *>(out.color)[gid] = hit ? color : make_float4(0, 0, 0, 0);
+}
+
+// The warp-synchronous march loop of the thread-per-ray kernels: every lane steps its ray until no lane of the warp is marching
+// any more.  Kept out of line so that the loop is register-allocated by itself - inlined into the 64-register kernel, next to the
+// block test, the ray was spilled and re-loaded inside the loop.  The ray travels through local memory once per call.
+// st: 0 marching, anything else: not marching (returned unchanged).
+template <bool DEEP>
+static __device__ __noinline__ int first_hit_march(const DScene &s, LeanRay *ray, int st) {
+    LeanRay r = *ray;
+    while (__any_sync(0xffffffffu, st == 0)) {
+#if CCU_FLAT_MARCH
+        if (!DEEP) st = lean_step_flat<false, CCU_FH_WARP_SKIP != 0>(s, s.air_top, r, st == 0, st);
+        else
+#endif
+        if (st == 0) st = lean_probe<DEEP, false>(s, s.air_top, r);
+    }
+    ray->t = r.t;
+    ray->steps = r.steps;
+    return st;
+}
+
 template <int MODE, bool HAS_BVH>
-__global__ void __launch_bounds__(256, CCU_FH_MIN_BLOCKS) k_first_hit(const __grid_constant__ DScene s, int seed, int n_pixels, int *block, int *face, int *node,
-                                                   int *kind, float *t, float *normal, float *color) {
-    stage_tables(s, nullptr);
+__global__ void __launch_bounds__(256, CCU_FH_MIN_BLOCKS) k_first_hit(const __grid_constant__ DScene s, int seed, int n_pixels, const __grid_constant__ FirstHitOut out) {
+    stage_tables_per_warp(s);
     const unsigned full = 0xffffffffu;
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = k < (unsigned)n_pixels;
-    const int gid = valid ? tile_order_pixel<true>(k, s.width, s.height) : 0;
+    unsigned px = 0, py = 0;
+    if (valid) tile_order_xy<true>(k, s.width, s.height, px, py);
+    const int gid = (int)(py * (unsigned)s.width + px);
     uint32_t rng = (uint32_t)seed + (uint32_t)gid;
     rng_next(rng);
     float3 o, d;
-    camera_ray<false>(s, gid, rng, o, d);
-    Record rec;
-    rec.distance = inff_(); rec.material = 0; rec.surf.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
-    rec.surf.color = make_float4(0, 0, 0, 0); rec.surf.emittance = 0;
-    HitInfo hi = {-1, 0, 0, 0, 0};
-    bool hit = false;
+    camera_ray_xy<false>(s, gid, (int)px, (int)py, rng, o, d);
     if (MODE == 0) {
+        Record rec;
+        rec.distance = inff_(); rec.material = 0; rec.surf.normal = f3(0, 0, 0); rec.point = f3(0, 0, 0);
+        rec.surf.color = make_float4(0, 0, 0, 0); rec.surf.emittance = 0;
+        HitInfo hi = {-1, 0, 0, 0, 0};
+        bool hit = false;
         if (valid) hit = HAS_BVH ? closest_intersect_ref(s, o, d, rec, hi) : octree_intersect_ref(s, o, d, rec, hi);
-        if (!HAS_BVH && hit) rec.point = o + d * (rec.distance - CCU_OFFSET);
-    } else {
-        March m;
-        const bool entered = march_begin(s, m, o, d, rec.distance);
-        LeanRay r;
-        r.o = m.o; r.d = m.d; r.inv = m.inv; r.t = m.t; r.limit = m.limit; r.steps = m.steps;
-        lean_prepare(r);
-        int st = (valid && entered) ? 0 : 2;      // 0 marching, 1 at a non-air leaf, 2 left the octree without a hit, 3 hit
-        for (;;) {
-            while (__any_sync(full, st == 0)) {
-#if CCU_FLAT_MARCH
-                if (MODE != 2) st = lean_step_flat<false>(s, s.air_top, r, st == 0, st);
-                else
-#endif
-                if (st == 0) st = lean_probe<MODE == 2, false>(s, s.air_top, r);
-            }
-            if (st == 1) {
-                m.t = r.t; m.steps = r.steps;
-                const Cell c = march_cell(m);
-                int level;
-                const int data = find_leaf_wide(s, c.bx, c.by, c.bz, level);
-                float th;
-                if (march_block(s, m, data, level, rec.surf, th)) {
-                    rec.distance = th;
-                    rec.material = data;
-                    hi.kind = 1;
-                    hi.bx = c.bx; hi.by = c.by; hi.bz = c.bz;
-                    st = 3;
-                } else {
-                    r.t = m.t; r.steps = m.steps;
-                    st = 0;
-                }
-            }
-            if (!__any_sync(full, st == 0)) break;
-        }
-        hit = st == 3;
-        if (HAS_BVH && valid) {
-            int bk = 0;
-            if (bvh_pair(s, o, d, rec.distance, rec.surf, bk)) { hit = true; hi.kind = bk; }
-        }
-        if (node && hit && hi.kind == 1) {
+        if (valid) first_hit_store(out, gid, hit, rec.material, rec.surf.normal, hi.node, hi.kind, rec.distance, rec.surf.color);
+        return;
+    }
+    March m;
+    const bool entered = march_begin(s, m, o, d, inff_());
+    LeanRay r;
+    r.o = m.o; r.d = m.d; r.inv = m.inv; r.t = m.t; r.limit = m.limit; r.steps = m.steps;
+    lean_prepare(r);
+    int st = (valid && entered) ? 0 : 2;      // 0 marching, 1 at a non-air leaf, 2 left the octree without a hit, 3 hit
+    // what an octree hit leaves behind; without BVHs it is written out at once, so that nothing of it stays in registers while
+    // the other lanes of the warp keep marching
+    Surf surf;
+    surf.normal = f3(0, 0, 0); surf.color = make_float4(0, 0, 0, 0); surf.emittance = 0;
+    float distance = inff_();
+    int material = 0, hbx = 0, hby = 0, hbz = 0;
+    for (;;) {
+        st = first_hit_march<MODE == 2>(s, &r, st);
+        if (st == 1) {
+            m.t = r.t; m.steps = r.steps;
+            const Cell c = march_cell(m);
             int level;
-            find_leaf(s, hi.bx, hi.by, hi.bz, level, hi.node);
+            const int data = find_leaf_wide(s, c.bx, c.by, c.bz, level);
+            float th;
+            Surf hs;
+            if (march_block(s, m, data, level, hs, th)) {
+                st = 3;
+                if (!HAS_BVH) {
+                    int hnode = -1;
+                    if (out.node) { int lv; find_leaf(s, c.bx, c.by, c.bz, lv, hnode); }
+                    first_hit_store(out, gid, true, data, hs.normal, hnode, 1, th, hs.color);
+                } else {
+                    surf = hs; distance = th; material = data;
+                    hbx = c.bx; hby = c.by; hbz = c.bz;
+                }
+            } else {
+                r.t = m.t; r.steps = m.steps;
+                st = 0;
+            }
         }
+        if (!__any_sync(full, st == 0)) break;
     }
     if (!valid) return;
-    if (block) block[gid] = hit ? rec.material : 0;
-    if (face) face[gid] = hit ? face_of(rec.surf.normal) : 6;
-    if (node) node[gid] = hit ? hi.node : -1;
-    if (kind) kind[gid] = hit ? hi.kind : 0;
-    if (t) t[gid] = hit ? rec.distance : inff_();
-    if (normal) {
-        normal[gid * 3 + 0] = hit ? rec.surf.normal.x : 0.0f;
-        normal[gid * 3 + 1] = hit ? rec.surf.normal.y : 0.0f;
-        normal[gid * 3 + 2] = hit ? rec.surf.normal.z : 0.0f;
+    if (!HAS_BVH) {
+        if (st != 3) first_hit_store(out, gid, false, 0, f3(0, 0, 0), -1, 0, inff_(), make_float4(0, 0, 0, 0));
+        return;
     }
-    if (color) {
-        float4 c = hit ? rec.surf.color : make_float4(0, 0, 0, 0);
-        reinterpret_cast<float4 *>(color)[gid] = c;
-    }
+    bool hit = st == 3;
+    int kind = hit ? 1 : 0, bk = 0;
+    if (bvh_pair(s, o, d, distance, surf, bk)) { hit = true; kind = bk; }
+    int hnode = -1;
+    if (out.node && hit && kind == 1) { int lv; find_leaf(s, hbx, hby, hbz, lv, hnode); }
+    first_hit_store(out, gid, hit, material, surf.normal, hnode, kind, distance, surf.color);
 }
 
 // rayTracer.cl:141-216
@@ -1272,7 +1302,8 @@ int ccu_first_hit(ccu_ctx *c, int32_t seed, int32_t *block, int32_t *face, int32
     const unsigned blocks = (unsigned)((n + 255) / 256);
     cudaEventRecord(c->ev0, c->stream);
     const bool fh_bvh = !(c->scene.world_bvh_empty && c->scene.actor_bvh_empty);
-#define CCU_FH(M, B) k_first_hit<M, B><<<blocks, 256, 0, c->stream>>>(c->scene, seed, (int)n, d_block, d_face, d_node, d_kind, d_t, d_normal, d_color)
+    const FirstHitOut fho = {d_block, d_face, d_node, d_kind, d_t, d_normal, d_color};
+#define CCU_FH(M, B) k_first_hit<M, B><<<blocks, 256, 0, c->stream>>>(c->scene, seed, (int)n, fho)
     if (fh_bvh) { if (mode == 0) CCU_FH(0, true); else if (mode == 1) CCU_FH(1, true); else CCU_FH(2, true); }
     else { if (mode == 0) CCU_FH(0, false); else if (mode == 1) CCU_FH(1, false); else CCU_FH(2, false); }
 #undef CCU_FH
