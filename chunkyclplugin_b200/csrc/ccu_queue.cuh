@@ -507,9 +507,9 @@ __device__ __forceinline__ bool q_stage_shade(const DScene &s, uint32_t *F, unsi
 // BVH stage: bvh.h:22-113 for the world BVH, then the actor BVH (kernel.h:17-18), on the commit-time layout
 // ------------------------------------------------------------------------------------------------------
 // Triangle_intersect (primitives.h:335-409) on a 32-byte aligned 24-word record (20 words + pad), three 256-bit loads
-__device__ __forceinline__ float triangle_hit_aligned(const int *__restrict__ t, float distance, float3 origin, float3 dir, float3 &normal,
+// q0: the record's first 32 bytes, loaded by the caller (one triangle ahead, so that the load is in flight during the previous test)
+__device__ __forceinline__ float triangle_hit_aligned(const Int8 &q0, const int *__restrict__ t, float distance, float3 origin, float3 dir, float3 &normal,
                                                       float &ou, float &ov, int &material) {
-    const Int8 q0 = ldg256(t);
     const int flags = q0.v[0];
     const float3 e1 = f3(i2f(q0.v[1]), i2f(q0.v[2]), i2f(q0.v[3]));
     const float3 e2 = f3(i2f(q0.v[4]), i2f(q0.v[5]), i2f(q0.v[6]));
@@ -693,16 +693,20 @@ __device__ __forceinline__ bool q_stage_leaf(const DScene &s, uint32_t *F, unsig
     // a shadow ray is answered by its first accepted triangle (see q_stage_resolve): the rest of the walk could only find a
     // closer one
     const bool first_hit_ends = CCU_SHADOW_SHORTCUT && (meta & QM_SHADOW) != 0;
+    // the head of the first triangle is requested together with the count word (a leaf block holds at least one triangle; the
+    // array is padded so that the read is in bounds even for an empty one), the head of triangle i + 1 while triangle i is tested
+    Int8 q0 = ldg256(blk + 8);
     for (int i = 0; i < num; i++) {
         float3 normal;
         float u, v;
         int material;
 #if CCU_BVH_PREFETCH & 4
-        // the second 32 bytes of this triangle (read after the determinant test) and the first 32 of the next one
+        // the second 32 bytes of this triangle (read after the determinant test)
         asm volatile("prefetch.global.L1 [%0];" :: "l"(blk + 8 + 24 * i + 8));
-        if (i + 1 < num) asm volatile("prefetch.global.L1 [%0];" :: "l"(blk + 8 + 24 * i + 24));
 #endif
-        const float t = triangle_hit_aligned(blk + 8 + 24 * i, dist, o, d, normal, u, v, material);
+        const Int8 q0_this = q0;
+        if (i + 1 < num) q0 = ldg256(blk + 8 + 24 * (i + 1));
+        const float t = triangle_hit_aligned(q0_this, blk + 8 + 24 * i, dist, o, d, normal, u, v, material);
         if (!is_nan(t) && material_sample(s, material, hit, u, v)) {
             hit.normal = normal;
             dist = t;
@@ -810,7 +814,7 @@ __device__ __forceinline__ void q_stage_bvh(const DScene &s, uint32_t *F, unsign
                     float3 normal;
                     float u, v;
                     int material;
-                    const float dist = triangle_hit_aligned(blk + 8 + 24 * i, b.dist, b.o, b.d, normal, u, v, material);
+                    const float dist = triangle_hit_aligned(ldg256(blk + 8 + 24 * i), blk + 8 + 24 * i, b.dist, b.o, b.d, normal, u, v, material);
                     if (!is_nan(dist) && material_sample(s, material, b.hit, u, v)) {
                         b.hit.normal = normal;
                         b.dist = dist;

@@ -852,6 +852,7 @@ int ccu_scene_commit(ccu_ctx *c) {
         c->world_root = wb.root;
         c->actor_root = ab.root;
         if (!c->use_bvh2) { wb.rec.clear(); ab.rec.clear(); tr.tris.clear(); }
+        tr.tris.insert(tr.tris.end(), 8, 0);      // the leaf stage reads the 32 bytes behind a count word before it looks at the count
         CU(c->world_rec.upload(wb.rec.data(), wb.rec.size(), c->stream));
         CU(c->actor_rec.upload(ab.rec.data(), ab.rec.size(), c->stream));
         CU(c->tris2.upload(tr.tris.data(), tr.tris.size(), c->stream));
