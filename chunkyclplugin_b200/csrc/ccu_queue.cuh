@@ -909,6 +909,13 @@ __device__ __forceinline__ int tile_order_pixel(unsigned k, int W, int H) {
 }
 
 // rayTracer.cl:109-112, then the next pass / pixel: rayTracer.cl:55-91
+// LAST_FIRST: the tile-order indices are handed out from the end.  A launch ends with the pixels drawn last still walking through
+// their passes one sample after the other (measured: 0.57 ms of a 16-pass 1080p launch, against 0.10 ms for a 1-pass one), so the
+// last pixels should be quick ones.  Without entity BVHs the quick pixels are the sky at the top of the frame (one ray), which
+// tile order starts with: config 1 -2.4 % per pass with the order reversed.  With BVHs every ray walks them and the sky is not
+// cheap any more (entity scene: +13 % reversed), so those kernels keep the forward order.  Orders derived from a measured per-chunk
+// cost (time between draws, or sample latency by chunk) were tried and cost more in the END stage than they gained.
+template <bool LAST_FIRST>
 __device__ __forceinline__ bool q_stage_end(const DScene &s, const PassParams &w, uint32_t *F, unsigned *mask, int *live, int lane, int min_lanes) {
     const unsigned full = 0xffffffffu;
     const int row = q_pop_batch(mask, QS_END, lane, min_lanes);
@@ -972,7 +979,7 @@ __device__ __forceinline__ bool q_stage_end(const DScene &s, const PassParams &w
             const int rank = __popc(want & ((1u << lane) - 1u));
             const unsigned k = rank < n1 ? base1 + (unsigned)rank : base2 + (unsigned)(rank - n1);
             if (k < (unsigned)w.n_pixels) {
-                gid = tile_order_pixel(k, s.width, s.height);
+                gid = tile_order_pixel(LAST_FIRST ? (unsigned)w.n_pixels - 1u - k : k, s.width, s.height);
                 pass = 0;
             } else {
                 alive = false;
@@ -1088,7 +1095,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, 1) k_render_queue(const __grid_c
             case QS_MARCH: QSTAT(0, 1); q_stage_march<NST, LAY>(s, top, F, mask, lane, qp.yield_below, qp.refill_min); break;
             case QS_BLOCK:
             case QS_EXIT: ran = q_stage_resolve<HAS_BVH>(s, F, mask, lane, best == QS_BLOCK, min_lanes); break;
-            case QS_END: ran = q_stage_end(s, qp.w, F, mask, live, lane, min_lanes); break;
+            case QS_END: ran = q_stage_end<!HAS_BVH>(s, qp.w, F, mask, live, lane, min_lanes); break;
 #if CCU_BVH_PARK
             case QS_BVH: QSTAT(16, 1); if (HAS_BVH) q_stage_bvh<NST>(s, F, mask, stk, qp.bvh_deep, lane, qp.yield_below, qp.refill_min); break;
             case QS_LEAF: if (HAS_BVH) ran = q_stage_leaf(s, F, mask, stk, qp.bvh_deep, lane, min_lanes); break;
