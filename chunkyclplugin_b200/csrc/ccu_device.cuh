@@ -61,9 +61,10 @@ struct DScene {
     const int *__restrict__ actor_bvh;
     const int *__restrict__ trigs;
     int world_bvh_empty, actor_bvh_empty;   // result of the bvh.h:23-32 probe, evaluated once at commit
-    // BVH stage layout (built at commit): 64-byte records {left box, right box, left ref, right ref, pad, pad} per inner
-    // node (two 256-bit loads), 32-byte aligned triangle blocks {count, 0 x 7} + count x 24 words (PackedTriangle's 20 words +
-    // pad: three 256-bit loads per triangle); ref >= 0 record, ref < 0: -(1 + block offset / 8 words)
+    // BVH stage layout (built at commit): one 64-byte record per inner node = two 32-byte halves of the same shape, {box (6 floats),
+    // ref, 0} of the first child and of the second child (a pair of lanes fetches a record with ONE L1 wavefront, ccu_queue.cuh);
+    // 32-byte aligned triangle blocks {count, 0 x 7} + count x 24 words (PackedTriangle's 20 words + pad: three 256-bit loads per
+    // triangle); ref >= 0 record, ref < 0: -(1 + block offset / 8 words)
     const int4 *__restrict__ world_rec;
     const int4 *__restrict__ actor_rec;
     const int *__restrict__ tris2;

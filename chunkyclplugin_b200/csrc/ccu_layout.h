@@ -293,14 +293,15 @@ int bvh_ref(const std::vector<int> &bvh, const std::vector<int> &trigs, size_t n
     if (left + 6 >= bvh.size() || right + 6 >= bvh.size()) { b.ok = false; return -1; }
     const size_t r = b.rec.size() / 16;
     b.rec.resize(b.rec.size() + 16, 0);
+    // two 32-byte halves of the same shape: {box (6 floats), ref, 0} of the first child, then of the second child
     for (int i = 0; i < 6; i++) {
         b.rec[r * 16 + i] = bvh[left + 1 + i];
-        b.rec[r * 16 + 6 + i] = bvh[right + 1 + i];
+        b.rec[r * 16 + 8 + i] = bvh[right + 1 + i];
     }
     const int rl = bvh_ref(bvh, trigs, left, depth + 1, b, tr, leaf_map);
     const int rr = bvh_ref(bvh, trigs, right, depth + 1, b, tr, leaf_map);
-    b.rec[r * 16 + 12] = rl;
-    b.rec[r * 16 + 13] = rr;
+    b.rec[r * 16 + 6] = rl;
+    b.rec[r * 16 + 14] = rr;
     return (int)r;
 }
 
