@@ -51,6 +51,11 @@
 #ifndef CCU_BVH_PAIR_LOADS
 #define CCU_BVH_PAIR_LOADS 0
 #endif
+// 1: the shadow-ray weight is recomputed instead of kept in a slot field (24 fields: with the top table read from global memory
+// the pool then fits the 100-KB shared-memory carve-out, which leaves 128 KB of L1 instead of 96)
+#ifndef CCU_Q_NO_SHW
+#define CCU_Q_NO_SHW 0
+#endif
 #ifndef CCU_MARCH_UNROLL
 #define CCU_MARCH_UNROLL 1
 #endif
@@ -85,7 +90,10 @@ constexpr int QS_COUNT = QS_BVH;   // stages of the kernels without BVHs
 // surface point of the current hit is the origin of the shadow ray and lives in QF_O*.
 enum QField : int {
     QF_GID = 0, QF_META, QF_RNG, QF_COLX, QF_COLY, QF_COLZ, QF_THRX, QF_THRY, QF_THRZ,
-    QF_SNX, QF_SNY, QF_SNZ, QF_SHW,
+    QF_SNX, QF_SNY, QF_SNZ,
+#if !CCU_Q_NO_SHW
+    QF_SHW,
+#endif
     QF_OX, QF_OY, QF_OZ, QF_DX, QF_DY, QF_DZ, QF_IX, QF_IY, QF_IZ, QF_T, QF_LIMIT, QF_STEPS,
     QF_COUNT,
     // HAS_BVH only: the closest hit so far while the ray is in the BVH / SHADE stages.  Its distance, emittance and normal.x
@@ -369,7 +377,14 @@ __device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *
         float3 throughput = f3(QFL(QF_THRX), QFL(QF_THRY), QFL(QF_THRZ));
         float3 color = f3(QFL(QF_COLX), QFL(QF_COLY), QFL(QF_COLZ));
         float3 sky = sky_radiance(s, d);
+#if CCU_Q_NO_SHW
+        // the shadow ray's weight |d . n| (sky.h:84) from the stored normal and the ray's direction, for every lane and then selected
+        // (under `if (shadow)` the compiler splits the sky code above into two copies)
+        const float shw = fabsf(dot3(d, f3(QFL(QF_SNX), QFL(QF_SNY), QFL(QF_SNZ))));
+        color = color + (sky * throughput) * (shadow ? shw : 1.0f);
+#else
         color = color + (sky * throughput) * (shadow ? QFL(QF_SHW) : 1.0f);
+#endif
         QFL(QF_COLX) = color.x; QFL(QF_COLY) = color.y; QFL(QF_COLZ) = color.z;
         if (shadow) bounce = true;
         else q_push(mask, QS_END, lane, row);
@@ -403,7 +418,9 @@ __device__ __forceinline__ void q_shade(const DScene &s, uint32_t *F, unsigned *
     if (sun) {
         QFL(QF_SNX) = normal.x; QFL(QF_SNY) = normal.y; QFL(QF_SNZ) = normal.z;
         next_d = sun_sample_direction_sc(s, x1, sn, cs);
+#if !CCU_Q_NO_SHW
         QFL(QF_SHW) = fabsf(dot3(next_d, normal));
+#endif
         QU(QF_META) = meta | QM_SHADOW;
         // the shadow ray starts at the surface point and inherits the surface hit's distance as its limit
         next_o = from;
