@@ -85,8 +85,13 @@ __device__ __forceinline__ int face_of(float3 n) {
 #ifndef CCU_FH_WARP_SKIP
 #define CCU_FH_WARP_SKIP 0
 #endif
+// threads per block of the first-hit kernel and resident blocks per SM (the warps of a block do not depend on each other, so
+// the block size only decides how many warps wait for the slowest one before their registers are handed on)
+#ifndef CCU_FH_THREADS
+#define CCU_FH_THREADS 128
+#endif
 #ifndef CCU_FH_MIN_BLOCKS
-#define CCU_FH_MIN_BLOCKS 4
+#define CCU_FH_MIN_BLOCKS (1024 / CCU_FH_THREADS)
 #endif
 struct FirstHitOut { int *block, *face, *node, *kind; float *t, *normal, *color; };
 __device__ __forceinline__ void first_hit_store(const FirstHitOut &out, int gid, bool hit, int material, float3 n, int node, int kind, float t, float4 color) {
@@ -123,7 +128,7 @@ static __device__ __noinline__ int first_hit_march(const DScene &s, LeanRay *ray
 }
 
 template <int MODE, bool HAS_BVH>
-__global__ void __launch_bounds__(256, CCU_FH_MIN_BLOCKS) k_first_hit(const __grid_constant__ DScene s, int seed, int n_pixels, const __grid_constant__ FirstHitOut out) {
+__global__ void __launch_bounds__(CCU_FH_THREADS, CCU_FH_MIN_BLOCKS) k_first_hit(const __grid_constant__ DScene s, int seed, int n_pixels, const __grid_constant__ FirstHitOut out) {
     stage_tables_per_warp(s);
     const unsigned full = 0xffffffffu;
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1300,11 +1305,11 @@ int ccu_first_hit(ccu_ctx *c, int32_t seed, int32_t *block, int32_t *face, int32
     float *d_normal = normal ? reinterpret_cast<float *>(scratch + 9 * n) : nullptr;
     fill_scene(c);
     const int mode = layout_mode(c);
-    const unsigned blocks = (unsigned)((n + 255) / 256);
+    const unsigned blocks = (unsigned)((n + CCU_FH_THREADS - 1) / CCU_FH_THREADS);
     cudaEventRecord(c->ev0, c->stream);
     const bool fh_bvh = !(c->scene.world_bvh_empty && c->scene.actor_bvh_empty);
     const FirstHitOut fho = {d_block, d_face, d_node, d_kind, d_t, d_normal, d_color};
-#define CCU_FH(M, B) k_first_hit<M, B><<<blocks, 256, 0, c->stream>>>(c->scene, seed, (int)n, fho)
+#define CCU_FH(M, B) k_first_hit<M, B><<<blocks, CCU_FH_THREADS, 0, c->stream>>>(c->scene, seed, (int)n, fho)
     if (fh_bvh) { if (mode == 0) CCU_FH(0, true); else if (mode == 1) CCU_FH(1, true); else CCU_FH(2, true); }
     else { if (mode == 0) CCU_FH(0, false); else if (mode == 1) CCU_FH(1, false); else CCU_FH(2, false); }
 #undef CCU_FH
