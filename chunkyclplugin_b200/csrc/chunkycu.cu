@@ -1461,6 +1461,32 @@ int ccu_bench_gather(ccu_ctx *c, int64_t array_bytes, int32_t dependent, float *
 // Host-only check of the commit-time traversal layouts (no CUDA call): for every voxel of `xyz` (count x 3 ints) returns what
 // the value-carrying layout (find_leaf_wide) and the march layout (lean_probe) answer, so that CPU tests can compare both
 // with the reference's root descent (octree.h:81-88).
+int ccu_debug_bvh_layout(const int32_t *bvh, int64_t n_bvh, const int32_t *trigs, int64_t n_trigs, int32_t *rec, int64_t rec_cap,
+                         int32_t *tris, int64_t tris_cap, int64_t *rec_words, int64_t *tris_words, int32_t *root, int32_t *ok) {
+    if (!bvh || n_bvh < 0 || n_trigs < 0 || (n_trigs > 0 && !trigs) || !rec_words || !tris_words || !root || !ok)
+        return fail(CCU_EINVAL, "ccu_debug_bvh_layout: bad argument");
+    const std::vector<int> nodes(bvh, bvh + n_bvh), tp(trigs, trigs + n_trigs);
+    BvhLayout b;
+    TriRepack tr;
+    std::unordered_map<int, int> leaf_map;
+    b.root = bvh_is_empty(nodes) ? 0 : bvh_ref(nodes, tp, 0, 0, b, tr, leaf_map);
+    if (!b.ok) { b.rec.clear(); tr.tris.clear(); }
+    tr.tris.insert(tr.tris.end(), 8, 0);        // as ccu_scene_commit does
+    *ok = b.ok ? 1 : 0;
+    *root = b.root;
+    *rec_words = (int64_t)b.rec.size();
+    *tris_words = (int64_t)tr.tris.size();
+    if (rec) {
+        if (rec_cap < (int64_t)b.rec.size()) return fail(CCU_EINVAL, "ccu_debug_bvh_layout: rec buffer too small");
+        std::copy(b.rec.begin(), b.rec.end(), rec);
+    }
+    if (tris) {
+        if (tris_cap < (int64_t)tr.tris.size()) return fail(CCU_EINVAL, "ccu_debug_bvh_layout: tris buffer too small");
+        std::copy(tr.tris.begin(), tr.tris.end(), tris);
+    }
+    return CCU_OK;
+}
+
 int ccu_debug_layout_lookup(const int32_t *tree, int64_t n, int32_t depth, const int32_t *xyz, int64_t count, int32_t *wide_value,
                             int32_t *wide_level, int32_t *air_solid, int32_t *air_level) {
     if (!tree || n < 1 || depth < 0 || depth > 30 || (count > 0 && !xyz)) return fail(CCU_EINVAL, "ccu_debug_layout_lookup: bad argument");

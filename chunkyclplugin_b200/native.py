@@ -84,6 +84,7 @@ SYMBOLS = {
     "ccu_tonemap": (C.c_int, [_vp, _i32, _i32, _f, _vp, _i32, _vp]),
     "ccu_bench_gather": (C.c_int, [_vp, _i64, _i32, C.POINTER(_f), C.POINTER(_f)]),
     "ccu_debug_layout_lookup": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "ccu_debug_bvh_layout": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, C.POINTER(_i64), C.POINTER(_i64), _pi32, _pi32]),
     # multi-GPU
     "ccu_group_create": (C.c_int, [_vp, _i32, C.POINTER(_vp)]),
     "ccu_group_unique_id": (C.c_int, [_vp]),
@@ -160,6 +161,21 @@ def layout_lookup(tree: np.ndarray, depth: int, xyz: np.ndarray):
     check(load().ccu_debug_layout_lookup(_ptr(tree), tree.size, depth, _ptr(xyz), n, _ptr(out["wide_value"]), _ptr(out["wide_level"]),
                                          _ptr(out["air_solid"]), _ptr(out["air_level"])))
     return out
+
+
+def debug_bvh_layout(bvh: np.ndarray, trigs: np.ndarray):
+    """The BVH stage layout the library builds at commit for a packed BVH node array + triangle palette (host only).
+    Returns (rec int32[n, 16], tris int32[...], root, ok)."""
+    bvh = np.ascontiguousarray(bvh, dtype=np.int32)
+    trigs = np.ascontiguousarray(trigs, dtype=np.int32)
+    nr, nt, root, ok = _i64(), _i64(), _i32(), _i32()
+    lib = load()
+    check(lib.ccu_debug_bvh_layout(_ptr(bvh), bvh.size, _ptr(trigs), trigs.size, None, 0, None, 0, C.byref(nr), C.byref(nt), C.byref(root), C.byref(ok)))
+    rec = np.zeros(max(nr.value, 1), dtype=np.int32)
+    tris = np.zeros(max(nt.value, 1), dtype=np.int32)
+    check(lib.ccu_debug_bvh_layout(_ptr(bvh), bvh.size, _ptr(trigs), trigs.size, _ptr(rec), rec.size, _ptr(tris), tris.size,
+                                   C.byref(nr), C.byref(nt), C.byref(root), C.byref(ok)))
+    return rec[:nr.value].reshape(-1, 16), tris[:nt.value], root.value, bool(ok.value)
 
 
 def device_count() -> int:

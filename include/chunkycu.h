@@ -159,6 +159,15 @@ int ccu_bench_gather(ccu_ctx *ctx, int64_t array_bytes, int32_t dependent, float
 int ccu_debug_layout_lookup(const int32_t *tree, int64_t n, int32_t depth, const int32_t *xyz, int64_t count, int32_t *wide_value,
                             int32_t *wide_level, int32_t *air_solid, int32_t *air_level);
 
+/* Test support, host only: the BVH stage layout ccu_scene_commit builds from a BinaryBVH.packed node array (bvh.h:47-110: 7 ints
+ * per node {child / -leaf pointer, 6 box floats}) and the triangle palette (count + n x 20 ints per leaf, PackedTriangle.java:46-78).
+ * rec: 16 words per inner node = two halves {box (6), ref, 0} of the first / second child; tris: per leaf {count, 0 x 7} +
+ * count x 24 words, 8 words of zero padding at the end; ref >= 0 = inner record, ref < 0 = -(1 + leaf block offset / 8 words).
+ * rec / tris may be NULL (sizes only); *ok = 0 when the node array cannot be laid out (malformed, or deeper than the 64 entries of
+ * the reference's traversal stack, bvh.h:38).  Used by the CPU test-suite. */
+int ccu_debug_bvh_layout(const int32_t *bvh, int64_t n_bvh, const int32_t *trigs, int64_t n_trigs, int32_t *rec, int64_t rec_cap,
+                         int32_t *tris, int64_t tris_cap, int64_t *rec_words, int64_t *tris_words, int32_t *root, int32_t *ok);
+
 /* ---- multi-GPU: samples-per-pixel split over the GPUs of one box -------------------------------------------
  * The reference is one JVM and one device (RendererInstance.java:81-101).  A group is N contexts, each holding a full scene
  * replica; pass p of a window goes to member p mod N with the seed it would have had on one GPU (state = seed_p + gid,
